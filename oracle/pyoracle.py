@@ -1,0 +1,165 @@
+"""ctypes loader for oracle/liboracle.so (TEST INFRASTRUCTURE — the checker, never the product).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this.  Arrays are numpy uint64, little-endian limbs: Fr = 4 limbs, Fp = 6, packed affine G1 =
+12 (x‖y), projective = 18 (X‖Y‖Z); all Montgomery unless a name says "canonical".
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_U64P = ctypes.POINTER(ctypes.c_uint64)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = [os.path.join(_HERE, f) for f in ("oracle.c", "mont.h", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = ctypes.CDLL(so)
+        _LIB.orc_init()
+    return _LIB
+
+
+def _p(a):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(_U64P)
+
+
+def _binop(name, w):
+    def f(a, b):
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, w)
+        b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, w)
+        o = np.empty_like(a)
+        getattr(lib(), name)(_p(a), _p(b), _p(o), ctypes.c_size_t(a.shape[0]))
+        return o
+    return f
+
+
+def _unop(name, w):
+    def f(a):
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, w)
+        o = np.empty_like(a)
+        getattr(lib(), name)(_p(a), _p(o), ctypes.c_size_t(a.shape[0]))
+        return o
+    return f
+
+
+fr_mul, fr_add, fr_sub = _binop("orc_fr_mul", 4), _binop("orc_fr_add", 4), _binop("orc_fr_sub", 4)
+fp_mul, fp_add, fp_sub = _binop("orc_fp_mul", 6), _binop("orc_fp_add", 6), _binop("orc_fp_sub", 6)
+fr_to_mont, fr_from_mont, fr_inv = _unop("orc_fr_to_mont", 4), _unop("orc_fr_from_mont", 4), _unop("orc_fr_inv", 4)
+fp_to_mont, fp_from_mont, fp_inv = _unop("orc_fp_to_mont", 6), _unop("orc_fp_from_mont", 6), _unop("orc_fp_inv", 6)
+
+
+def fr_consts():
+    m, r1, r2, root, gen = (np.zeros(4, np.uint64) for _ in range(5))
+    inv = ctypes.c_uint64()
+    lib().orc_fr_consts(_p(m), ctypes.byref(inv), _p(r1), _p(r2), _p(root), _p(gen))
+    return {"modulus": m, "inv": inv.value, "r1": r1, "r2": r2, "root_of_unity": root, "generator": gen}
+
+
+def fp_consts():
+    m, r1, r2 = (np.zeros(6, np.uint64) for _ in range(3))
+    inv = ctypes.c_uint64()
+    lib().orc_fp_consts(_p(m), ctypes.byref(inv), _p(r1), _p(r2))
+    return {"modulus": m, "inv": inv.value, "r1": r1, "r2": r2}
+
+
+def random_fr(seed, n):
+    """n uniform values in [0, r) as raw limbs (n, 4) — same stream as model.random_fr."""
+    out = np.empty((n, 4), np.uint64)
+    lib().orc_random_fr(ctypes.c_uint64(seed), ctypes.c_size_t(n), _p(out))
+    return out
+
+
+def g1_generator():
+    out = np.empty(12, np.uint64)
+    lib().orc_g1_generator(_p(out))
+    return out
+
+
+def g1_on_curve(xy):
+    xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(-1, 12)
+    return bool(lib().orc_g1_on_curve(_p(xy), ctypes.c_size_t(xy.shape[0])))
+
+
+def g1_proj_to_affine_canonical(xyz):
+    """(is_identity, x_int, y_int) from a projective Montgomery X‖Y‖Z."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.uint64).reshape(18)
+    out = np.empty(12, np.uint64)
+    inf = lib().orc_g1_proj_to_affine_canonical(_p(xyz), _p(out))
+    if inf:
+        return None
+    return (limbs_to_int(out[:6]), limbs_to_int(out[6:]))
+
+
+def synthetic_bases(n, a=0xB2000001, d=0x9E3779B1):
+    out = np.empty((n, 12), np.uint64)
+    lib().orc_synthetic_bases(ctypes.c_size_t(n), ctypes.c_uint64(a), ctypes.c_uint64(d), _p(out))
+    return out
+
+
+def msm_variable_base(points, scalars_mont, threads=1):
+    points = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 12)
+    scalars_mont = np.ascontiguousarray(scalars_mont, dtype=np.uint64).reshape(-1, 4)
+    assert points.shape[0] == scalars_mont.shape[0]
+    out = np.empty(18, np.uint64)
+    lib().orc_msm_variable_base(_p(points), _p(scalars_mont), ctypes.c_size_t(points.shape[0]), _p(out),
+                                ctypes.c_int(threads))
+    return out
+
+
+def msm_naive(points, scalars_mont):
+    points = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 12)
+    scalars_mont = np.ascontiguousarray(scalars_mont, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty(18, np.uint64)
+    lib().orc_msm_naive(_p(points), _p(scalars_mont), ctypes.c_size_t(points.shape[0]), _p(out))
+    return out
+
+
+def ntt(data, inverse=False, coset=False, threads=1):
+    """EvaluationDomain fft / ifft / coset_fft / coset_ifft on a power-of-two (n, 4) Montgomery array."""
+    a = np.array(data, dtype=np.uint64).reshape(-1, 4)
+    n = a.shape[0]
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n
+    rc = lib().orc_ntt(_p(a), ctypes.c_uint32(log_n), int(inverse), int(coset), int(threads))
+    if rc != 0:
+        raise ValueError("InvalidEvalDomainSize")
+    return a
+
+
+def domain(log_n):
+    g, gi, si, geni = (np.zeros(4, np.uint64) for _ in range(4))
+    rc = lib().orc_domain(ctypes.c_uint32(log_n), _p(g), _p(gi), _p(si), _p(geni))
+    if rc != 0:
+        raise ValueError("InvalidEvalDomainSize")
+    return {"group_gen": g, "group_gen_inv": gi, "size_inv": si, "generator_inv": geni}
+
+
+def limbs_to_int(l):
+    v = 0
+    for i, x in enumerate(np.asarray(l).reshape(-1)):
+        v |= int(x) << (64 * i)
+    return v
+
+
+def int_to_limbs(v, n):
+    return np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)], dtype=np.uint64)
+
+
+def ints_to_limbs(vals, n):
+    return np.array([[(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)] for v in vals], dtype=np.uint64).reshape(-1, n)
