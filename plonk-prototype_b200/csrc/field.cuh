@@ -86,59 +86,62 @@ struct Field {
     PB_HD Field neg() const { return is_zero() ? *this : (zero() - *this); }
     PB_HD Field dbl() const { return *this + *this; }
 
-    // acc[0..N) += Σ_{j even} x[j]·y·2^(32j); carry-out left in the flag.
-    PB_HD static void chain_mad(uint32_t *acc, const uint32_t *x, uint32_t y) {
-        acc[0] = cc::mad_lo_cc(x[0], y, acc[0]);
-        acc[1] = cc::madc_hi_cc(x[0], y, acc[1]);
+    // ---- multiplication: u64 column accumulators -------------------------------------------------
+    // The running value is held as E + O·2^32 with E, O arrays of H = N/2 u64 columns: E[k] covers
+    // limb positions (2k, 2k+1), O[k] positions (2k+1, 2k+2).  a[even]·b_i lands column-aligned in E,
+    // a[odd]·b_i column-aligned in O, so every row is one add.cc.u64/addc.cc.u64 chain over
+    // mul.wide.u32 products (→ IMAD.WIDE.U32.X).
+    static constexpr int H = N / 2;
+
+    // One Montgomery elimination step: adds m·p with m = −E[0]·p⁻¹ mod 2^32 so position 0 becomes 0.
+    // p's limbs are compile-time immediates.  The E chain's carry-out (position N) is the high half
+    // of O[H−1].  O's own carry-out is provably 0 (capacity argument in DESIGN.md).
+    PB_HD static void redc_step(uint64_t *E, uint64_t *O) {
+        if (P::LOW_LIMBS_1_FFFFFFFF) {
+            // Fr: p ≡ 2^64 − 2^32 + 1 (mod 2^64), −p⁻¹ ≡ −1 (mod 2^32) ⇒ m = −e0 and the two low partial
+            // products need no multiplier: m·p[0] = m (e0 + m = 2^32·nz), m·p[1] = (m−nz)·2^32 + e0,
+            // with nz = (e0 ≠ 0).
+            uint32_t e0 = cc::lo32(E[0]);
+            uint32_t m = 0u - e0;
+            (void)cc::add_cc(e0, m);
+            uint32_t nz = cc::addc(0, 0);
+            O[0] = cc::add_cc64(O[0], cc::pack64(e0, m - nz));
 #pragma unroll
-        for (int j = 2; j < N; j += 2) {
-            acc[j] = cc::madc_lo_cc(x[j], y, acc[j]);
-            acc[j + 1] = cc::madc_hi_cc(x[j], y, acc[j + 1]);
+            for (int k = 1; k < H; k++) O[k] = cc::addc_cc64(O[k], cc::mul_wide(P::mod(2 * k + 1), m));
+            E[0] = cc::add_cc64(cc::pack64(0, cc::hi32(E[0])), cc::pack64(0, nz));
+#pragma unroll
+            for (int k = 1; k < H; k++) E[k] = cc::addc_cc64(E[k], cc::mul_wide(P::mod(2 * k), m));
+        } else {
+            uint32_t m = cc::lo32(E[0]) * P::INV32;
+            O[0] = cc::add_cc64(O[0], cc::mul_wide(P::mod(1), m));
+#pragma unroll
+            for (int k = 1; k < H; k++) O[k] = cc::addc_cc64(O[k], cc::mul_wide(P::mod(2 * k + 1), m));
+            E[0] = cc::add_cc64(E[0], cc::mul_wide(P::mod(0), m));
+#pragma unroll
+            for (int k = 1; k < H; k++) E[k] = cc::addc_cc64(E[k], cc::mul_wide(P::mod(2 * k), m));
         }
+        O[H - 1] = cc::pack64(cc::lo32(O[H - 1]), cc::addc(cc::hi32(O[H - 1]), 0));
     }
-    // One Montgomery elimination step on T = E + O·2^32: adds m·p with m = −E[0]/p mod 2^32, so E[0]
-    // becomes 0.  p's limbs are compile-time immediates.
-    PB_HD static void redc_step(uint32_t *E, uint32_t *O) {
-        uint32_t m = cc::mul_lo(E[0], P::INV32);
-        O[0] = cc::mad_lo_cc(P::mod(1), m, O[0]);
-        O[1] = cc::madc_hi_cc(P::mod(1), m, O[1]);
+    // Round i ≥ 1.  On entry position 0 of S is zero and the value (already divided by 2^32) is
+    // (S >> 32) + D·(one position down).  S's position 1 is folded into D's position 0, S is rebuilt
+    // one column lower as the new odd accumulator, D becomes the new even accumulator.
+    PB_HD static void round(uint64_t *S, uint64_t *D, const uint32_t *a, uint32_t bi) {
+        uint32_t d0 = cc::add_cc(cc::lo32(D[0]), cc::hi32(S[0]));  // carry → start of the odd chain
 #pragma unroll
-        for (int j = 2; j < N; j += 2) {
-            O[j] = cc::madc_lo_cc(P::mod(j + 1), m, O[j]);
-            O[j + 1] = cc::madc_hi_cc(P::mod(j + 1), m, O[j + 1]);
-        }
-        E[0] = cc::mad_lo_cc(P::mod(0), m, E[0]);
-        E[1] = cc::madc_hi_cc(P::mod(0), m, E[1]);
+        for (int k = 0; k < H - 1; k++) S[k] = cc::addc_cc64(S[k + 1], cc::mul_wide(a[2 * k + 1], bi));
+        S[H - 1] = cc::addc64(cc::mul_wide(a[N - 1], bi), 0);
+        D[0] = cc::add_cc64(cc::pack64(d0, cc::hi32(D[0])), cc::mul_wide(a[0], bi));
 #pragma unroll
-        for (int j = 2; j < N; j += 2) {
-            E[j] = cc::madc_lo_cc(P::mod(j), m, E[j]);
-            E[j + 1] = cc::madc_hi_cc(P::mod(j), m, E[j + 1]);
-        }
-        O[N - 1] = cc::addc(O[N - 1], 0);
-    }
-    // Round i ≥ 1.  On entry the running value (already divided by 2^32) is  S[1..] + D, where S is
-    // the array whose limb 0 was just zeroed.  On exit D plays S's role for the next round.
-    PB_HD static void round(uint32_t *S, uint32_t *D, const uint32_t *a, uint32_t bi) {
-        D[0] = cc::add_cc(D[0], S[1]);  // fold S[1] into the new even accumulator, carry → odd chain
-#pragma unroll
-        for (int j = 0; j < N - 2; j += 2) {  // new odd accumulator = S[2..] + a[odd]·bi, written over S
-            S[j] = cc::madc_lo_cc(a[j + 1], bi, S[j + 2]);
-            S[j + 1] = cc::madc_hi_cc(a[j + 1], bi, S[j + 3]);
-        }
-        S[N - 2] = cc::madc_lo_cc(a[N - 1], bi, 0);
-        S[N - 1] = cc::madc_hi(a[N - 1], bi, 0);
-        chain_mad(D, a, bi);  // even accumulator += a[even]·bi
-        S[N - 1] = cc::addc(S[N - 1], 0);
+        for (int k = 1; k < H; k++) D[k] = cc::addc_cc64(D[k], cc::mul_wide(a[2 * k], bi));
+        S[H - 1] = cc::pack64(cc::lo32(S[H - 1]), cc::addc(cc::hi32(S[H - 1]), 0));
         redc_step(D, S);
     }
     PB_HD friend Field operator*(const Field &a, const Field &b) {
-        uint32_t A[N], B[N];  // A: even accumulator first, B: odd accumulator first
+        uint64_t A[H], B[H];
 #pragma unroll
-        for (int j = 0; j < N; j += 2) {
-            A[j] = cc::mul_lo(a.l[j], b.l[0]);
-            A[j + 1] = cc::mul_hi(a.l[j], b.l[0]);
-            B[j] = cc::mul_lo(a.l[j + 1], b.l[0]);
-            B[j + 1] = cc::mul_hi(a.l[j + 1], b.l[0]);
+        for (int k = 0; k < H; k++) {
+            A[k] = cc::mul_wide(a.l[2 * k], b.l[0]);
+            B[k] = cc::mul_wide(a.l[2 * k + 1], b.l[0]);
         }
         redc_step(A, B);
 #pragma unroll
@@ -147,12 +150,16 @@ struct Field {
             round(B, A, a.l, b.l[i + 1]);
         }
         round(A, B, a.l, b.l[N - 1]);
-        // the last round left B with limb 0 cleared: value = B[1..] + A  (< 2p)
+        // the last round cleared position 0 of B: value = (B >> 32) + A  (< 2p), merged limb-wise
         Field r;
-        r.l[0] = cc::add_cc(A[0], B[1]);
+        r.l[0] = cc::add_cc(cc::lo32(A[0]), cc::hi32(B[0]));
 #pragma unroll
-        for (int k = 1; k < N - 1; k++) r.l[k] = cc::addc_cc(A[k], B[k + 1]);
-        r.l[N - 1] = cc::addc(A[N - 1], 0);
+        for (int k = 1; k < N - 1; k++) {
+            uint32_t x = (k & 1) ? cc::hi32(A[k >> 1]) : cc::lo32(A[k >> 1]);
+            uint32_t y = (k & 1) ? cc::lo32(B[(k + 1) >> 1]) : cc::hi32(B[k >> 1]);
+            r.l[k] = cc::addc_cc(x, y);
+        }
+        r.l[N - 1] = cc::addc(cc::hi32(A[H - 1]), 0);
         return reduce_once(r);
     }
     PB_HD Field sqr() const { return *this * *this; }
@@ -193,6 +200,7 @@ struct Field {
 struct FrParams {
     static constexpr int N = 8;
     static constexpr uint32_t INV32 = 0xffffffffu;
+    static constexpr bool LOW_LIMBS_1_FFFFFFFF = true;
     PB_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t v[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
                                    0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
@@ -213,6 +221,7 @@ struct FrParams {
 struct FpParams {
     static constexpr int N = 12;
     static constexpr uint32_t INV32 = 0xfffcfffdu;
+    static constexpr bool LOW_LIMBS_1_FFFFFFFF = false;
     PB_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t v[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
                                     0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
