@@ -1,0 +1,111 @@
+/* pb200.h — C ABI of the B200-native MSM / NTT prover backend.
+ *
+ * The reference (/root/reference, Manta-Network/Plonk-Prototype) has no FFI or plugin interface of its
+ * own: its hot path lives in two functions of crates pinned by /root/reference/Cargo.toml:19-20
+ *   - dusk_bls12_381::multiscalar_mul::msm_variable_base(&[G1Affine], &[Scalar]) -> G1Projective
+ *   - dusk_plonk::fft::EvaluationDomain::{new, fft, ifft, coset_fft, coset_ifft}
+ * (§8b).  The entry points below are what a `-sys` crate patched into
+ * those two functions would bind; INTEGRATION.md shows the Rust side.  Every entry point cites the
+ * upstream function it replaces.
+ *
+ * Conventions
+ *   - Scalars: 4 × u64 little-endian limbs, Montgomery form (a·2^256 mod r), fully reduced — the
+ *     memory image of `Scalar.0` / `BlsScalar.0`.
+ *   - Points: packed affine x[6] ‖ y[6] u64 limbs, Montgomery form (a·2^384 mod p), 96 bytes.  The
+ *     identity is not encodable; callers drop identity bases (an SRS never holds one).
+ *   - MSM result: projective X ‖ Y ‖ Z (18 × u64, Montgomery) normalised so Z = R (Montgomery 1) for
+ *     a finite point and (0, R, 0) for the identity — i.e. the unique affine value embedded in
+ *     `G1Projective`, which is what `G1Affine::from` / `to_bytes` would produce from any equal point.
+ *   - All functions return 0 on success, non-zero on failure (pb200_last_error has the text).  No
+ *     exception, abort or CPU fallback ever crosses this boundary; a missing GPU is an error.
+ *   - A context is bound to one CUDA device and one stream and is not thread-safe.
+ */
+#ifndef PB200_H
+#define PB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PB200_API __attribute__((visibility("default")))
+#else
+#define PB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pb200_ctx pb200_ctx;
+typedef struct pb200_srs pb200_srs;
+
+enum {
+    PB200_OK = 0,
+    PB200_ERR_ARG = 1,      /* bad argument (null pointer, log_n >= 32, range outside the SRS …) */
+    PB200_ERR_CUDA = 2,     /* a CUDA runtime call or kernel failed */
+    PB200_ERR_NO_DEVICE = 3 /* no usable sm_100 device */
+};
+
+/* ---- context ---------------------------------------------------------------------------------- */
+PB200_API int pb200_init(pb200_ctx **out, int device_id);
+PB200_API void pb200_destroy(pb200_ctx *ctx);
+PB200_API const char *pb200_last_error(const pb200_ctx *ctx);
+/* The CUDA stream (cudaStream_t) every call of this context is ordered on. */
+PB200_API void *pb200_stream(pb200_ctx *ctx);
+PB200_API int pb200_sync(pb200_ctx *ctx);
+
+/* ---- device buffers (for callers that keep polynomials resident between calls) ---------------- */
+PB200_API int pb200_malloc(pb200_ctx *ctx, void **dev_ptr, size_t bytes);
+PB200_API int pb200_free(pb200_ctx *ctx, void *dev_ptr);
+PB200_API int pb200_h2d(pb200_ctx *ctx, void *dev_dst, const void *host_src, size_t bytes);
+PB200_API int pb200_d2h(pb200_ctx *ctx, void *host_dst, const void *dev_src, size_t bytes);
+
+/* ---- NTT: dusk_plonk::fft::EvaluationDomain ------------------- */
+/* EvaluationDomain::new(num_coeffs): size = next power of two, error when log2(size) >= 32.
+ * Writes log2(size) to *log_n. */
+PB200_API int pb200_domain_log_size(size_t num_coeffs, uint32_t *log_n);
+/* EvaluationDomain::{fft_in_place, ifft_in_place, coset_fft_in_place, coset_ifft_in_place} on a HOST
+ * vector of exactly 2^log_n scalars (the Rust shim zero-pads shorter inputs as upstream does).
+ *   inverse = 0, coset = 0 : fft          out[i] = Σ_j a_j ω^{ij}
+ *   inverse = 1, coset = 0 : ifft         ω → ω⁻¹, then × n⁻¹
+ *   inverse = 0, coset = 1 : coset_fft    a_j ← a_j·7^j, then fft
+ *   inverse = 1, coset = 1 : coset_ifft   ifft, then a_j ← a_j·7^{-j}
+ * Natural order in, natural order out.  Blocks until the result is in `data`. */
+PB200_API int pb200_ntt(pb200_ctx *ctx, uint64_t *data_host, uint32_t log_n, int inverse, int coset);
+/* Same transform on a DEVICE-resident vector, in place, ordered on the context stream (no sync). */
+PB200_API int pb200_ntt_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, int inverse, int coset);
+
+/* ---- MSM: dusk_bls12_381::multiscalar_mul::msm_variable_base ---- */
+/* Upload bases once (CommitKey::powers_of_g); they stay resident for every later commit. */
+PB200_API int pb200_srs_upload(pb200_ctx *ctx, const uint64_t *xy_mont_host, size_t n_points, pb200_srs **out);
+/* Wrap bases that are already on the device (n_points × 96 B, not copied, not freed by srs_free). */
+PB200_API int pb200_srs_wrap_dev(pb200_ctx *ctx, const uint64_t *xy_mont_dev, size_t n_points, pb200_srs **out);
+PB200_API void pb200_srs_free(pb200_ctx *ctx, pb200_srs *srs);
+PB200_API size_t pb200_srs_len(const pb200_srs *srs);
+/* msm_variable_base(&points[offset .. offset + n], scalars): Σ scalars[i]·points[offset + i].
+ * Scalars on the HOST; n = 0 or all-zero scalars give the identity.  Blocks; result on the host. */
+PB200_API int pb200_msm_g1(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_mont_host, size_t n,
+                 uint64_t out_xyz_mont[18]);
+/* Same with scalars already on the DEVICE (n × 32 B).  Blocks; result on the host. */
+PB200_API int pb200_msm_g1_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_mont_dev, size_t n,
+                     uint64_t out_xyz_mont[18]);
+/* Pippenger window width used for n points (exposed for the benches' work model). */
+PB200_API uint32_t pb200_msm_window_bits(size_t n);
+
+/* ---- synthetic workloads & measurement helpers (bench.py / tests) -------------- */
+/* bases[i] = (a + i·d)·G, packed affine Montgomery, written to a device buffer of n × 96 B. */
+PB200_API int pb200_synthetic_bases_dev(pb200_ctx *ctx, uint64_t *xy_mont_dev, size_t n, uint64_t a, uint64_t d);
+/* Per-kernel device time of the most recent MSM / NTT call, from CUDA events on the context stream.
+ * Known names: "msm.accumulate", "msm.sort", "msm.reduce", "msm.total", "ntt.total".
+ * Profiling must have been switched on before that call. */
+PB200_API int pb200_profile_enable(pb200_ctx *ctx, int on);
+PB200_API int pb200_profile_ms(pb200_ctx *ctx, const char *name, float *ms);
+/* Number of kernels this library has launched on the context since init (bench.py's gpu_launches). */
+PB200_API uint64_t pb200_launch_count(const pb200_ctx *ctx);
+/* Integer-pipe microbenchmark: sustained IMAD.WIDE.U32 (32×32+64) lane-operations per second over
+ * the whole chip — the denominator of the MSM / NTT integer rooflines. */
+PB200_API int pb200_imad_peak(pb200_ctx *ctx, double *wide_lane_ops_per_s, double *sm_clock_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PB200_H */

@@ -1,0 +1,184 @@
+"""ctypes binding of libpb200.so (the C ABI in include/pb200.h).
+
+There is no fallback of any kind: if the shared library is missing, or no sm_100 GPU is present,
+creating a Context raises.  Nothing in this package imports oracle/.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpb200.so")
+_lib = None
+
+EXPORTS = [
+    "pb200_init", "pb200_destroy", "pb200_last_error", "pb200_stream", "pb200_sync",
+    "pb200_malloc", "pb200_free", "pb200_h2d", "pb200_d2h",
+    "pb200_domain_log_size", "pb200_ntt", "pb200_ntt_dev",
+    "pb200_srs_upload", "pb200_srs_wrap_dev", "pb200_srs_free", "pb200_srs_len",
+    "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_window_bits",
+    "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_launch_count",
+    "pb200_imad_peak",
+]
+
+
+class Pb200Error(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Pb200Error("libpb200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                             "there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, u64p = ctypes.c_void_p, ctypes.c_void_p
+        L.pb200_init.argtypes = [ctypes.POINTER(vp), ctypes.c_int]
+        L.pb200_destroy.argtypes = [vp]
+        L.pb200_destroy.restype = None
+        L.pb200_last_error.argtypes = [vp]
+        L.pb200_last_error.restype = ctypes.c_char_p
+        L.pb200_stream.argtypes = [vp]
+        L.pb200_stream.restype = vp
+        L.pb200_sync.argtypes = [vp]
+        L.pb200_malloc.argtypes = [vp, ctypes.POINTER(vp), ctypes.c_size_t]
+        L.pb200_free.argtypes = [vp, vp]
+        L.pb200_h2d.argtypes = [vp, vp, vp, ctypes.c_size_t]
+        L.pb200_d2h.argtypes = [vp, vp, vp, ctypes.c_size_t]
+        L.pb200_domain_log_size.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)]
+        L.pb200_ntt.argtypes = [vp, u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
+        L.pb200_ntt_dev.argtypes = [vp, u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
+        L.pb200_srs_upload.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.POINTER(vp)]
+        L.pb200_srs_wrap_dev.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.POINTER(vp)]
+        L.pb200_srs_free.argtypes = [vp, vp]
+        L.pb200_srs_free.restype = None
+        L.pb200_srs_len.argtypes = [vp]
+        L.pb200_srs_len.restype = ctypes.c_size_t
+        L.pb200_msm_g1.argtypes = [vp, vp, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]
+        L.pb200_msm_g1_dev.argtypes = [vp, vp, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]
+        L.pb200_msm_window_bits.argtypes = [ctypes.c_size_t]
+        L.pb200_msm_window_bits.restype = ctypes.c_uint32
+        L.pb200_synthetic_bases_dev.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64]
+        L.pb200_profile_enable.argtypes = [vp, ctypes.c_int]
+        L.pb200_profile_ms.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_float)]
+        L.pb200_launch_count.argtypes = [vp]
+        L.pb200_launch_count.restype = ctypes.c_uint64
+        L.pb200_imad_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    """Address of a numpy array (host) or an int device pointer."""
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return ctypes.c_void_p(a.ctypes.data)
+    return ctypes.c_void_p(int(a))
+
+
+class Context:
+    """One CUDA device + stream (pb200_ctx)."""
+
+    def __init__(self, device=0):
+        self._h = ctypes.c_void_p()
+        rc = lib().pb200_init(ctypes.byref(self._h), int(device))
+        if rc != 0:
+            msg = lib().pb200_last_error(self._h).decode() if self._h else "no usable sm_100 GPU"
+            if self._h:
+                lib().pb200_destroy(self._h)
+                self._h = ctypes.c_void_p()
+            raise Pb200Error("pb200_init failed (%d): %s — there is no CPU fallback" % (rc, msg))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().pb200_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise Pb200Error("pb200 error %d: %s" % (rc, lib().pb200_last_error(self._h).decode()))
+
+    # -- plumbing
+    @property
+    def stream(self):
+        return lib().pb200_stream(self._h)
+
+    def sync(self):
+        self._check(lib().pb200_sync(self._h))
+
+    def malloc(self, nbytes):
+        p = ctypes.c_void_p()
+        self._check(lib().pb200_malloc(self._h, ctypes.byref(p), nbytes))
+        return p.value
+
+    def free(self, dev):
+        self._check(lib().pb200_free(self._h, ctypes.c_void_p(dev)))
+
+    def h2d(self, dev, host):
+        self._check(lib().pb200_h2d(self._h, ctypes.c_void_p(dev), _ptr(host), host.nbytes))
+
+    def d2h(self, host, dev):
+        self._check(lib().pb200_d2h(self._h, _ptr(host), ctypes.c_void_p(dev), host.nbytes))
+
+    # -- NTT
+    def ntt(self, data_host, log_n, inverse=False, coset=False):
+        assert data_host.dtype == np.uint64 and data_host.size == 4 << log_n
+        self._check(lib().pb200_ntt(self._h, _ptr(data_host), log_n, int(inverse), int(coset)))
+
+    def ntt_dev(self, dev, log_n, inverse=False, coset=False):
+        self._check(lib().pb200_ntt_dev(self._h, ctypes.c_void_p(dev), log_n, int(inverse), int(coset)))
+
+    # -- MSM
+    def srs_upload(self, xy_host):
+        assert xy_host.dtype == np.uint64 and xy_host.size % 12 == 0
+        h = ctypes.c_void_p()
+        self._check(lib().pb200_srs_upload(self._h, _ptr(xy_host), xy_host.size // 12, ctypes.byref(h)))
+        return h
+
+    def srs_wrap_dev(self, dev, n):
+        h = ctypes.c_void_p()
+        self._check(lib().pb200_srs_wrap_dev(self._h, ctypes.c_void_p(dev), n, ctypes.byref(h)))
+        return h
+
+    def srs_free(self, srs):
+        lib().pb200_srs_free(self._h, srs)
+
+    def msm(self, srs, scalars_host, offset=0):
+        n = scalars_host.size // 4
+        out = np.zeros(18, np.uint64)
+        self._check(lib().pb200_msm_g1(self._h, srs, offset, _ptr(scalars_host), n, _ptr(out)))
+        return out
+
+    def msm_dev(self, srs, scalars_dev, n, offset=0):
+        out = np.zeros(18, np.uint64)
+        self._check(lib().pb200_msm_g1_dev(self._h, srs, offset, ctypes.c_void_p(scalars_dev), n, _ptr(out)))
+        return out
+
+    def synthetic_bases_dev(self, dev, n, a=0xB2000001, d=0x9E3779B1):
+        self._check(lib().pb200_synthetic_bases_dev(self._h, ctypes.c_void_p(dev), n, a, d))
+
+    # -- measurement
+    def profile_enable(self, on=True):
+        self._check(lib().pb200_profile_enable(self._h, int(on)))
+
+    def profile_ms(self, name):
+        v = ctypes.c_float()
+        self._check(lib().pb200_profile_ms(self._h, name.encode(), ctypes.byref(v)))
+        return v.value
+
+    def launch_count(self):
+        return int(lib().pb200_launch_count(self._h))
+
+    def imad_peak(self):
+        ops, mhz = ctypes.c_double(), ctypes.c_double()
+        self._check(lib().pb200_imad_peak(self._h, ctypes.byref(ops), ctypes.byref(mhz)))
+        return ops.value, mhz.value

@@ -31,8 +31,8 @@ PB_HD uint64_t mul_wide(uint32_t a, uint32_t b) { uint64_t r; asm("mul.wide.u32 
 PB_HD uint64_t add_cc64(uint64_t a, uint64_t b) { uint64_t r; asm volatile("add.cc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 PB_HD uint64_t addc_cc64(uint64_t a, uint64_t b) { uint64_t r; asm volatile("addc.cc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 PB_HD uint64_t addc64(uint64_t a, uint64_t b) { uint64_t r; asm volatile("addc.u64 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-PB_HD uint32_t lo32(uint64_t x) { uint32_t l, h; asm("mov.b64 {%0, %1}, %2;" : "=r"(l), "=r"(h) : "l"(x)); return l; }
-PB_HD uint32_t hi32(uint64_t x) { uint32_t l, h; asm("mov.b64 {%0, %1}, %2;" : "=r"(l), "=r"(h) : "l"(x)); return h; }
+PB_HD uint32_t lo32(uint64_t x) { return (uint32_t)x; }
+PB_HD uint32_t hi32(uint64_t x) { return (uint32_t)(x >> 32); }
 PB_HD uint64_t pack64(uint32_t l, uint32_t h) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(l), "r"(h)); return r; }
 }  // namespace cc
 #elif defined(PB200_HOST_EMU)

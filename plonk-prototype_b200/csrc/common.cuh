@@ -1,0 +1,101 @@
+// common.cuh — context object, error plumbing and launch bookkeeping shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pb200.h"
+
+struct NttPlan;  // ntt.cu
+
+struct pb200_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    bool profile = false;
+    std::map<std::string, float> prof_ms;
+    // NTT state
+    std::map<uint32_t, NttPlan *> ntt_plans;  // key: log_n | inverse << 8 | coset << 9
+    void *ntt_scratch = nullptr;
+    size_t ntt_scratch_bytes = 0;
+    // MSM workspace (grown on demand, reused across calls)
+    void *msm_ws = nullptr;
+    size_t msm_ws_bytes = 0;
+    void *pinned = nullptr;  // small pinned staging block for results
+    size_t pinned_bytes = 0;
+};
+
+struct pb200_srs {
+    const uint64_t *dev = nullptr;
+    size_t n = 0;
+    bool owned = false;
+};
+
+inline int pb_fail(pb200_ctx *ctx, int code, const char *what, const char *detail, const char *file, int line) {
+    if (ctx) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "%s: %s (%s:%d)", what, detail ? detail : "", file, line);
+        ctx->err = buf;
+    }
+    return code;
+}
+#define PB_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+#define PB_ARG(ctx, cond)                                                                           \
+    do {                                                                                            \
+        if (!(cond)) return pb_fail(ctx, PB200_ERR_ARG, "bad argument", #cond, __FILE__, __LINE__); \
+    } while (0)
+#define PB_TRY(expr)            \
+    do {                        \
+        int rc__ = (expr);      \
+        if (rc__) return rc__;  \
+    } while (0)
+// After a kernel launch: count it and surface launch-configuration errors.
+#define PB_LAUNCHED(ctx)                                                                            \
+    do {                                                                                            \
+        (ctx)->launches++;                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                                       \
+        if (e__ != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "kernel launch", cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+// Scoped CUDA-event timer feeding pb200_profile_ms (only when profiling is on).
+struct PbTimer {
+    pb200_ctx *ctx;
+    const char *name;
+    cudaEvent_t a = nullptr, b = nullptr;
+    PbTimer(pb200_ctx *c, const char *n) : ctx(c), name(n) {
+        if (ctx->profile) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, ctx->stream);
+        }
+    }
+    void stop() {
+        if (a && b) cudaEventRecord(b, ctx->stream);
+    }
+    // Call after the stream has been synchronised.
+    void collect() {
+        if (a && b) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) ctx->prof_ms[name] = ms;
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+            a = b = nullptr;
+        }
+    }
+    ~PbTimer() {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+};
+
+int pb_ensure(pb200_ctx *ctx, void **buf, size_t *have, size_t need);  // api.cu

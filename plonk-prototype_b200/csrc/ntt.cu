@@ -1,0 +1,436 @@
+// ntt.cu — radix-2 NTT / iNTT / coset-NTT over the BLS12-381 scalar field for sm_100a.
+//
+// Replaces dusk-plonk 0.8.2 `fft::EvaluationDomain::{fft, ifft, coset_fft, coset_ifft}` (crate pinned
+// at /root/reference/Cargo.toml:19; algorithm restated in SURVEY.md App. B.2 and oracle/oracle.c).
+// Natural order in, natural order out, bit-exact (outputs are fully reduced field elements).
+//
+// Structure: a four-step decomposition n = n1·n2(·n3) with at most three passes
+// over HBM.  Every pass stages a tile of 2^S points × C columns in shared memory (limb-planar,
+// skewed against bank conflicts), runs S decimation-in-frequency stages as radix-8 register
+// butterflies with one shared-memory exchange per three stages, and writes the tile back with the
+// bit-reversal, the inter-pass twiddle ω_n^{j·k}, the coset powers 7^{±j} and the n⁻¹ scaling fused
+// into the load / store.  Tiles are contiguous along the column axis, so global accesses are
+// C·32-byte runs (one 32-byte sector per element at worst).
+#include <algorithm>
+#include <cstring>
+#include "common.cuh"
+#include "field.cuh"
+
+namespace {
+
+constexpr uint32_t kTileLogMax = 11;  // 2^11 elements × 32 B = 64 KiB of shared memory per CTA
+constexpr uint32_t kTwoAdicity = 32;
+
+struct NttPass {
+    uint32_t S;          // log2 of the sub-transform length
+    uint32_t logC;       // log2 of columns per CTA
+    uint32_t type;       // 0: strided sub-transform, in place (column axis contiguous)
+                         // 1: contiguous sub-transform, output transposed to natural order
+    uint32_t ncol_log;   // type 0: log2(columns per row block)
+    uint32_t nrows_log;  // type 1: log2(number of rows) = log n − S
+    uint32_t n1_log;     // type 1: log2 of the first-pass length (row ↔ natural-index digit swap)
+    uint32_t load_mode;  // 0 none | 1 × lo[e]·hi[e] with e = natural input index        (coset_fft)
+    uint32_t store_mode; // 0 none | 1 × constant | 2 × pow(col·k << mult_log) | 3 × pow(natural output index)
+    uint32_t mult_log;
+    uint32_t l_B, s_B;   // split point of the two-level power tables
+    const Fr *tw;        // ω_{2^S}^j, j < 2^(S−1)
+    const Fr *l_lo, *l_hi, *s_lo, *s_hi;
+    const Fr *s_const;
+};
+
+__device__ __forceinline__ Fr g_load(const Fr *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = q[0], b = q[1];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void g_store(Fr *p, const Fr &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+// Shared-memory tile: 8 limb planes of PS words; element i lives at word i + (i >> 5) of each plane.
+__device__ __forceinline__ Fr sm_load(const uint32_t *sm, uint32_t PS, uint32_t i) {
+    uint32_t s = i + (i >> 5);
+    Fr r;
+#pragma unroll
+    for (int w = 0; w < 8; w++) r.l[w] = sm[w * PS + s];
+    return r;
+}
+__device__ __forceinline__ void sm_store(uint32_t *sm, uint32_t PS, uint32_t i, const Fr &v) {
+    uint32_t s = i + (i >> 5);
+#pragma unroll
+    for (int w = 0; w < 8; w++) sm[w * PS + s] = v.l[w];
+}
+__device__ __forceinline__ Fr pow2level(const Fr *lo, const Fr *hi, uint32_t B, uint32_t e) {
+    Fr a = g_load(lo + (e & ((1u << B) - 1)));
+    Fr b = g_load(hi + (e >> B));
+    return a * b;
+}
+// DIF butterfly: (a, b) ← (a + b, (a − b)·w)
+__device__ __forceinline__ void bfly(Fr &a, Fr &b, const Fr &w) {
+    Fr s = a + b;
+    Fr d = a - b;
+    a = s;
+    b = d * w;
+}
+__device__ __forceinline__ void bfly1(Fr &a, Fr &b) {  // w = 1
+    Fr s = a + b;
+    b = a - b;
+    a = s;
+}
+
+__global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const Fr *__restrict__ in, Fr *__restrict__ out, NttPass p) {
+    extern __shared__ uint32_t sm[];
+    const uint32_t S = p.S, logC = p.logC, C = 1u << logC;
+    const uint32_t T = 1u << (S + logC), PS = T + (T >> 5) + 1;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x;
+
+    // ---- tile geometry
+    uint64_t in_base;       // address of (x = 0, c = 0)
+    uint32_t rowrev0 = 0;   // type 1: natural-order row digit of column 0
+    uint32_t col0 = 0;      // type 0: column index of c = 0 inside its row block
+    if (p.type == 0) {
+        uint32_t blocks_per_row_log = p.ncol_log - logC;
+        uint32_t R = blockIdx.x >> blocks_per_row_log;
+        col0 = (blockIdx.x & ((1u << blocks_per_row_log) - 1)) << logC;
+        in_base = ((uint64_t)R << (S + p.ncol_log)) + col0;
+    } else {
+        rowrev0 = blockIdx.x << logC;
+        in_base = 0;
+    }
+    const uint32_t n2_log = p.nrows_log - p.n1_log;
+
+    // ---- phase 1: global → shared (coalesced along the contiguous axis), optional coset scaling
+    for (uint32_t i = tid; i < T; i += nthr) {
+        uint32_t x, c;
+        uint64_t addr;
+        if (p.type == 0) {
+            c = i & (C - 1);
+            x = i >> logC;
+            addr = in_base + ((uint64_t)x << p.ncol_log) + c;
+        } else {
+            x = i & ((1u << S) - 1);
+            c = i >> S;
+            uint32_t rr = rowrev0 + c;
+            uint32_t row = ((rr & ((1u << p.n1_log) - 1)) << n2_log) + (rr >> p.n1_log);
+            addr = ((uint64_t)row << S) + x;
+        }
+        Fr v = g_load(in + addr);
+        if (p.load_mode == 1) v = v * pow2level(p.l_lo, p.l_hi, p.l_B, (uint32_t)addr);
+        sm_store(sm, PS, (x << logC) + c, v);
+    }
+    __syncthreads();
+
+    // ---- phase 2: S DIF stages, three per round, eight points per thread
+    {
+        const uint32_t c = tid & (C - 1), tx = tid >> logC;
+        int b_top = (int)S - 1;
+        while (b_top >= 3) {  // general round on bits [b_lo, b_lo+2], b_lo ≥ 1
+            const uint32_t b_lo = (uint32_t)b_top - 2;
+            const uint32_t v = tx & ((1u << b_lo) - 1), u = tx >> b_lo;
+            const uint32_t xbase = (u << (b_lo + 3)) | v;
+            Fr a[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) a[e] = sm_load(sm, PS, ((xbase | ((uint32_t)e << b_lo)) << logC) + c);
+            {
+                const uint32_t sh = S - 3 - b_lo;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    Fr w = g_load(p.tw + ((((uint32_t)e << b_lo) | v) << sh));
+                    bfly(a[e], a[e + 4], w);
+                }
+            }
+            {
+                const uint32_t sh = S - 2 - b_lo;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    Fr w = g_load(p.tw + ((((uint32_t)e << b_lo) | v) << sh));
+                    bfly(a[e], a[e + 2], w);
+                    bfly(a[e + 4], a[e + 6], w);
+                }
+            }
+            {
+                Fr w = g_load(p.tw + (v << (S - 1 - b_lo)));
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) bfly(a[e], a[e + 1], w);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++) sm_store(sm, PS, ((xbase | ((uint32_t)e << b_lo)) << logC) + c, a[e]);
+            __syncthreads();
+            b_top -= 3;
+        }
+        {  // last round on bits [0, 2]: only stages b_top … 0 remain and their twiddles are constants
+            const uint32_t xbase = tx << 3;
+            Fr a[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) a[e] = sm_load(sm, PS, ((xbase | (uint32_t)e) << logC) + c);
+            if (b_top >= 2) {
+                bfly1(a[0], a[4]);
+#pragma unroll
+                for (int e = 1; e < 4; e++) {
+                    Fr w = g_load(p.tw + ((uint32_t)e << (S - 3)));
+                    bfly(a[e], a[e + 4], w);
+                }
+            }
+            if (b_top >= 1) {
+                Fr w4 = g_load(p.tw + (1u << (S - 2)));
+                bfly1(a[0], a[2]);
+                bfly1(a[4], a[6]);
+                bfly(a[1], a[3], w4);
+                bfly(a[5], a[7], w4);
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e += 2) bfly1(a[e], a[e + 1]);
+#pragma unroll
+            for (int e = 0; e < 8; e++) sm_store(sm, PS, ((xbase | (uint32_t)e) << logC) + c, a[e]);
+            __syncthreads();
+        }
+    }
+
+    // ---- phase 3: shared → global; position x holds output index k = bitrev_S(x)
+    for (uint32_t i = tid; i < T; i += nthr) {
+        const uint32_t c = i & (C - 1), x = i >> logC;
+        const uint32_t k = __brev(x) >> (32 - S);
+        Fr v = sm_load(sm, PS, i);
+        uint64_t addr;
+        if (p.type == 0) {
+            addr = in_base + ((uint64_t)k << p.ncol_log) + c;
+            if (p.store_mode == 2) v = v * pow2level(p.s_lo, p.s_hi, p.s_B, ((col0 + c) * k) << p.mult_log);
+        } else {
+            addr = (uint64_t)(rowrev0 + c) + ((uint64_t)k << p.nrows_log);
+            if (p.store_mode == 3) v = v * pow2level(p.s_lo, p.s_hi, p.s_B, (uint32_t)addr);
+        }
+        if (p.store_mode == 1) v = v * g_load(p.s_const);
+        g_store(out + addr, v);
+    }
+}
+
+// Domains of 1, 2 or 4 points: one thread evaluates the definition directly.
+__global__ void ntt_tiny_kernel(Fr *data, uint32_t log_n, int inverse, int coset, const Fr *consts) {
+    const uint32_t n = 1u << log_n;
+    Fr w = g_load(consts + 0), ninv = g_load(consts + 1), g = g_load(consts + 2);
+    Fr a[4], o[4];
+    for (uint32_t j = 0; j < n; j++) a[j] = g_load(data + j);
+    if (coset && !inverse) {
+        Fr pw = Fr::one();
+        for (uint32_t j = 0; j < n; j++) { a[j] = a[j] * pw; pw = pw * g; }
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        Fr acc = Fr::zero(), wi = w.pow_u64(i), pw = Fr::one();
+        for (uint32_t j = 0; j < n; j++) { acc = acc + a[j] * pw; pw = pw * wi; }
+        o[i] = acc;
+    }
+    if (inverse) {
+        Fr pw = ninv;
+        for (uint32_t i = 0; i < n; i++) { o[i] = o[i] * pw; if (coset) pw = pw * g; }
+    }
+    for (uint32_t i = 0; i < n; i++) g_store(data + i, o[i]);
+}
+
+// consts[0] = ω_n (or ω_n⁻¹ when inverse), [1] = n⁻¹, [2] = 7 (or 7⁻¹ when inverse), [3] = 1
+__global__ void ntt_consts_kernel(Fr *consts, uint32_t log_n, int inverse) {
+    Fr seven = Fr::zero();
+    seven.l[0] = 7;
+    seven = seven.to_mont();
+    // (r − 1) >> 32
+    const uint32_t e[7] = {0xffffffffu, 0xfffe5bfeu, 0x53bda402u, 0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+    Fr root = seven.pow(e, 7);  // primitive 2^32-th root of unity
+    Fr w = root;
+    for (uint32_t i = log_n; i < kTwoAdicity; i++) w = w.sqr();
+    Fr two = Fr::one().dbl();
+    Fr ninv = two.inv().pow_u64(log_n);
+    Fr g = seven;
+    if (inverse) { w = w.inv(); g = g.inv(); }
+    g_store(consts + 0, w);
+    g_store(consts + 1, ninv);
+    g_store(consts + 2, g);
+    g_store(consts + 3, Fr::one());
+}
+// out[j] = pre · base^(j·stride)
+__global__ void fill_powers_kernel(Fr *out, uint32_t count, const Fr *base, uint64_t stride, const Fr *pre) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    Fr b = g_load(base), p = g_load(pre);
+    g_store(out + j, p * b.pow_u64((uint64_t)j * stride));
+}
+
+}  // namespace
+
+struct NttPlan {
+    uint32_t log_n = 0;
+    int inverse = 0, coset = 0;
+    int n_pass = 0;
+    NttPass pass[3];
+    Fr *consts = nullptr;
+    std::vector<void *> allocs;
+};
+
+static int fill_powers(pb200_ctx *ctx, NttPlan *pl, Fr **out, uint32_t count, const Fr *base, uint64_t stride, const Fr *pre) {
+    void *buf = nullptr;
+    PB_CUDA(ctx, cudaMalloc(&buf, (size_t)count * sizeof(Fr)));
+    pl->allocs.push_back(buf);
+    fill_powers_kernel<<<(count + 127) / 128, 128, 0, ctx->stream>>>((Fr *)buf, count, base, stride, pre);
+    PB_LAUNCHED(ctx);
+    *out = (Fr *)buf;
+    return 0;
+}
+
+static int ntt_build_plan(pb200_ctx *ctx, uint32_t L, int inverse, int coset, NttPlan **out) {
+    NttPlan *pl = new NttPlan();
+    pl->log_n = L;
+    pl->inverse = inverse;
+    pl->coset = coset;
+    *out = pl;  // owned by the ctx map from here on (freed in ntt_free_plans even on error)
+    ctx->ntt_plans[L | ((uint32_t)inverse << 8) | ((uint32_t)coset << 9)] = pl;
+    void *cbuf = nullptr;
+    PB_CUDA(ctx, cudaMalloc(&cbuf, 4 * sizeof(Fr)));
+    pl->allocs.push_back(cbuf);
+    pl->consts = (Fr *)cbuf;
+    ntt_consts_kernel<<<1, 1, 0, ctx->stream>>>(pl->consts, L, inverse);
+    PB_LAUNCHED(ctx);
+    const Fr *c_w = pl->consts + 0, *c_ninv = pl->consts + 1, *c_g = pl->consts + 2, *c_one = pl->consts + 3;
+    if (L < 3) { pl->n_pass = 0; return 0; }
+
+    const int P = L <= kTileLogMax ? 1 : (L <= 2 * kTileLogMax ? 2 : 3);
+    uint32_t S[3] = {0, 0, 0};
+    if (P == 1) S[0] = L;
+    else if (P == 2) { S[0] = (L + 1) / 2; S[1] = L - S[0]; }
+    else { S[0] = (L + 2) / 3; S[1] = (L - S[0] + 1) / 2; S[2] = L - S[0] - S[1]; }
+    pl->n_pass = P;
+    const uint32_t B = (L + 1) / 2;  // two-level tables: lo has 2^B entries, hi 2^(L−B)
+
+    Fr *lo = nullptr, *hi_plain = nullptr, *hi_scaled = nullptr, *clo = nullptr, *chi = nullptr;
+    if (P >= 2) {
+        PB_TRY(fill_powers(ctx, pl, &lo, 1u << B, c_w, 1, c_one));
+        PB_TRY(fill_powers(ctx, pl, &hi_plain, 1u << (L - B), c_w, 1ull << B, c_one));
+        hi_scaled = hi_plain;
+        if (inverse && !coset) PB_TRY(fill_powers(ctx, pl, &hi_scaled, 1u << (L - B), c_w, 1ull << B, c_ninv));
+    }
+    if (coset) {
+        PB_TRY(fill_powers(ctx, pl, &clo, 1u << B, c_g, 1, c_one));
+        PB_TRY(fill_powers(ctx, pl, &chi, 1u << (L - B), c_g, 1ull << B, inverse ? c_ninv : c_one));
+    }
+    uint32_t done = 0;  // bits already transformed by earlier passes
+    for (int i = 0; i < P; i++) {
+        NttPass &p = pl->pass[i];
+        memset(&p, 0, sizeof(p));
+        p.S = S[i];
+        Fr *tw = nullptr;
+        PB_TRY(fill_powers(ctx, pl, &tw, 1u << (S[i] - 1), c_w, 1ull << (L - S[i]), c_one));
+        p.tw = tw;
+        const bool last = (i == P - 1);
+        if (!last) {
+            p.type = 0;
+            p.ncol_log = L - done - S[i];
+            p.logC = std::min(kTileLogMax - S[i], p.ncol_log);
+            p.store_mode = 2;
+            p.mult_log = done;  // ω_m^{j·k} with m = n / 2^done equals ω_n^{(j·k) << done}
+            p.s_lo = lo;
+            p.s_hi = (i == 0) ? hi_scaled : hi_plain;
+            p.s_B = B;
+        } else {
+            p.type = 1;
+            p.nrows_log = L - S[i];
+            p.n1_log = (P == 3) ? S[0] : p.nrows_log;
+            p.logC = std::min(kTileLogMax - S[i], p.nrows_log);
+            if (inverse && coset) { p.store_mode = 3; p.s_lo = clo; p.s_hi = chi; p.s_B = B; }
+            else if (inverse && P == 1) { p.store_mode = 1; p.s_const = c_ninv; }
+        }
+        if (i == 0 && coset && !inverse) { p.load_mode = 1; p.l_lo = clo; p.l_hi = chi; p.l_B = B; }
+        done += S[i];
+    }
+    return 0;
+}
+
+void ntt_free_plans(pb200_ctx *ctx) {
+    for (auto &kv : ctx->ntt_plans) {
+        for (void *a : kv.second->allocs) cudaFree(a);
+        delete kv.second;
+    }
+    ctx->ntt_plans.clear();
+    if (ctx->ntt_scratch) cudaFree(ctx->ntt_scratch);
+    ctx->ntt_scratch = nullptr;
+    ctx->ntt_scratch_bytes = 0;
+}
+
+static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset) {
+    if (L == 0) return 0;  // a one-point domain: every variant is the identity map
+    NttPlan *pl = nullptr;
+    auto it = ctx->ntt_plans.find(L | ((uint32_t)inverse << 8) | ((uint32_t)coset << 9));
+    if (it != ctx->ntt_plans.end()) pl = it->second;
+    else PB_TRY(ntt_build_plan(ctx, L, inverse, coset, &pl));
+    PbTimer timer(ctx, "ntt.total");
+    if (pl->n_pass == 0) {
+        ntt_tiny_kernel<<<1, 1, 0, ctx->stream>>>(data, L, inverse, coset, pl->consts);
+        PB_LAUNCHED(ctx);
+    } else {
+        const size_t bytes = sizeof(Fr) << L;
+        Fr *scratch = nullptr;
+        if (pl->n_pass > 1) {
+            PB_TRY(pb_ensure(ctx, &ctx->ntt_scratch, &ctx->ntt_scratch_bytes, bytes));
+            scratch = (Fr *)ctx->ntt_scratch;
+        }
+        for (int i = 0; i < pl->n_pass; i++) {
+            const NttPass &p = pl->pass[i];
+            const uint32_t tile_log = p.S + p.logC;
+            const uint32_t T = 1u << tile_log;
+            const size_t smem = (size_t)8 * (T + (T >> 5) + 1) * sizeof(uint32_t);
+            const uint32_t threads = T >> 3, blocks = 1u << (L - tile_log);
+            // pass 0 reads the caller's vector, the last pass writes it; intermediates live in scratch
+            const Fr *src = (i == 0) ? data : scratch;
+            Fr *dst = (i == pl->n_pass - 1) ? data : scratch;
+            ntt_pass_kernel<<<blocks, threads, smem, ctx->stream>>>(src, dst, p);
+            PB_LAUNCHED(ctx);
+        }
+    }
+    timer.stop();
+    if (ctx->profile) {
+        PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        timer.collect();
+    }
+    return 0;
+}
+
+int ntt_module_init(pb200_ctx *ctx) {
+    PB_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      8 * ((1 << kTileLogMax) + (1 << (kTileLogMax - 5)) + 1) * 4));
+    return 0;
+}
+
+extern "C" int pb200_domain_log_size(size_t num_coeffs, uint32_t *log_n) {
+    if (!log_n) return PB200_ERR_ARG;
+    uint32_t l = 0;
+    while (((size_t)1 << l) < num_coeffs) l++;
+    if (l >= kTwoAdicity) return PB200_ERR_ARG;  // EvaluationDomain::new → Err(InvalidEvalDomainSize)
+    *log_n = l;
+    return 0;
+}
+extern "C" int pb200_ntt_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, int inverse, int coset) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, data_dev != nullptr);
+    PB_ARG(ctx, log_n < kTwoAdicity);
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ntt_run(ctx, (Fr *)data_dev, log_n, inverse ? 1 : 0, coset ? 1 : 0);
+}
+extern "C" int pb200_ntt(pb200_ctx *ctx, uint64_t *data_host, uint32_t log_n, int inverse, int coset) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, data_host != nullptr);
+    PB_ARG(ctx, log_n < kTwoAdicity);
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)32 << log_n;
+    void *dev = nullptr;
+    PB_CUDA(ctx, cudaMallocAsync(&dev, bytes, ctx->stream));
+    int rc = 0;
+    cudaError_t e = cudaMemcpyAsync(dev, data_host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) rc = ntt_run(ctx, (Fr *)dev, log_n, inverse ? 1 : 0, coset ? 1 : 0);
+    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(data_host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFreeAsync(dev, ctx->stream);
+    if (rc) return rc;
+    if (e != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "pb200_ntt copy", cudaGetErrorString(e), __FILE__, __LINE__);
+    if (e2 != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "pb200_ntt sync", cudaGetErrorString(e2), __FILE__, __LINE__);
+    return 0;
+}

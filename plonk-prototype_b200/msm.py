@@ -1,0 +1,52 @@
+"""Host-side mirror of dusk-bls12_381 0.8 `multiscalar_mul::msm_variable_base` (pinned at
+/root/reference/Cargo.toml:20) on top of the C ABI.
+
+`msm_variable_base(points, scalars)`: points an (n, 12) uint64 array of packed affine Montgomery
+x‖y, scalars an (n, 4) uint64 array of Montgomery limbs; returns the projective X‖Y‖Z (18 limbs,
+normalised, Z = 0 for the identity).  Like upstream it is infallible for well-formed input and treats
+an empty input as the identity.  `CommitKey` keeps the bases resident on the GPU the way dusk-plonk's
+`CommitKey::powers_of_g` is held across commits.
+"""
+import numpy as np
+
+from . import _native
+from .domain import default_context
+
+
+def msm_variable_base(points, scalars, ctx=None):
+    ctx = ctx or default_context()
+    points = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 12)
+    scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    assert points.shape[0] == scalars.shape[0]
+    if points.shape[0] == 0:
+        out = np.zeros(18, np.uint64)
+        return ctx.msm(None, scalars)  # the library returns the identity for n = 0
+    srs = ctx.srs_upload(points)
+    try:
+        return ctx.msm(srs, scalars)
+    finally:
+        ctx.srs_free(srs)
+
+
+class CommitKey:
+    """`CommitKey { powers_of_g }` with the powers resident in HBM; `commit` = one MSM over the prefix."""
+
+    def __init__(self, powers_of_g, ctx=None):
+        self.ctx = ctx or default_context()
+        pts = np.ascontiguousarray(powers_of_g, dtype=np.uint64).reshape(-1, 12)
+        self.n = pts.shape[0]
+        self._srs = self.ctx.srs_upload(pts)
+
+    def max_degree(self):
+        return self.n - 1
+
+    def commit(self, coeffs):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+        if coeffs.shape[0] > self.n:
+            raise ValueError("PolynomialDegreeTooLarge")  # dusk-plonk `check_degree_is_within_bounds`
+        return self.ctx.msm(self._srs, coeffs)
+
+    def close(self):
+        if self._srs is not None:
+            self.ctx.srs_free(self._srs)
+            self._srs = None
