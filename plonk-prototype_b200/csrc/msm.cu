@@ -1,11 +1,636 @@
-// msm.cu — placeholder until the Pippenger pipeline lands (next commit).
+// msm.cu — variable-base multi-scalar multiplication over BLS12-381 G1 for sm_100a.
+//
+// Replaces dusk-bls12_381 0.8 `multiscalar_mul::msm_variable_base(&[G1Affine], &[Scalar]) -> G1Projective`
+// (crate pinned at /root/reference/Cargo.toml:20; upstream algorithm restated in SURVEY.md App. B.1 and
+// oracle/oracle.c).  The result is a group element, so it is compared after normalisation to affine.
+//
+// Pipeline — everything stays on the device, no host round trip until the result:
+//   1. count    scalars → canonical → signed c-bit digits; histogram of (window, |digit|) buckets
+//   2. scan     exclusive prefix sum of the histogram → bucket offsets
+//   3. scatter  (bucket id, point index | sign) entries, grouped by bucket           ("sort by bucket")
+//   4. accumulate  segmented reduction over the entry list: every thread owns a fixed-length segment
+//                  (perfect balance whatever the digit distribution), sums runs of equal bucket id with
+//                  mixed XYZZ+affine additions, writes complete runs to their bucket and emits ≤ 2
+//                  boundary partials; partials are reduced by the same scheme, level by level
+//   5. reduce   Σ_b b·B_b per window as chunked running sums, then a per-window tree sum
+//   6. combine  Horner over the windows (c doublings each), normalise to affine
+#include <algorithm>
+#include <cstring>
+
 #include "common.cuh"
+#include "g1.cuh"
+
+namespace {
+
+constexpr uint32_t kInvalid = 0xffffffffu;
+constexpr uint32_t kScanItems = 4, kScanThreads = 1024, kScanTile = kScanItems * kScanThreads;
+
+struct MsmCfg {
+    uint32_t n;       // points in this piece (< 2^27)
+    uint32_t c;       // window bits
+    uint32_t W;       // windows = ceil(256 / c)
+    uint32_t nb_log;  // log2 buckets per window = c − 1
+    uint32_t L1, L2;  // segment length at level 1 / higher levels
+    uint32_t K_log;   // log2 buckets per reduction chunk
+};
+
+// ------------------------------------------------------------------------------------------ loads
+__device__ __forceinline__ Fr load_fr(const uint64_t *scalars, size_t i) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(scalars + 4 * i);
+    uint4 a = q[0], b = q[1];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void load_fp2(const uint4 *q, Fp &a, Fp &b) {
+    uint4 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3], v4 = q[4], v5 = q[5];
+    a.l[0] = v0.x; a.l[1] = v0.y; a.l[2] = v0.z; a.l[3] = v0.w; a.l[4] = v1.x; a.l[5] = v1.y;
+    a.l[6] = v1.z; a.l[7] = v1.w; a.l[8] = v2.x; a.l[9] = v2.y; a.l[10] = v2.z; a.l[11] = v2.w;
+    b.l[0] = v3.x; b.l[1] = v3.y; b.l[2] = v3.z; b.l[3] = v3.w; b.l[4] = v4.x; b.l[5] = v4.y;
+    b.l[6] = v4.z; b.l[7] = v4.w; b.l[8] = v5.x; b.l[9] = v5.y; b.l[10] = v5.z; b.l[11] = v5.w;
+}
+__device__ __forceinline__ void store_fp2(uint4 *q, const Fp &a, const Fp &b) {
+    q[0] = make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]);
+    q[1] = make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]);
+    q[2] = make_uint4(a.l[8], a.l[9], a.l[10], a.l[11]);
+    q[3] = make_uint4(b.l[0], b.l[1], b.l[2], b.l[3]);
+    q[4] = make_uint4(b.l[4], b.l[5], b.l[6], b.l[7]);
+    q[5] = make_uint4(b.l[8], b.l[9], b.l[10], b.l[11]);
+}
+__device__ __forceinline__ G1Affine load_affine(const G1Affine *bases, uint32_t idx_sign) {
+    G1Affine p;
+    load_fp2(reinterpret_cast<const uint4 *>(bases + (idx_sign & 0x7fffffffu)), p.x, p.y);
+    if (idx_sign >> 31) p.y = p.y.neg();
+    return p;
+}
+__device__ __forceinline__ G1Xyzz load_xyzz(const G1Xyzz *p) {
+    G1Xyzz r;
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    load_fp2(q, r.x, r.y);
+    load_fp2(q + 6, r.zz, r.zzz);
+    return r;
+}
+__device__ __forceinline__ void store_xyzz(G1Xyzz *p, const G1Xyzz &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    store_fp2(q, v.x, v.y);
+    store_fp2(q + 6, v.zz, v.zzz);
+}
+
+// --------------------------------------------------------------------------------- digit recoding
+// Signed-digit decomposition of a canonical 255-bit scalar into W digits of c bits:
+// digit ∈ [−2^(c−1), 2^(c−1)]; the top window is never recoded (W·c ≥ 256 leaves it a spare bit).
+template <class F>
+__device__ __forceinline__ void for_each_digit(const Fr &canon, uint32_t c, uint32_t W, F &&f) {
+    const uint32_t half = 1u << (c - 1), mask = (1u << c) - 1;
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < W; w++) {
+        const uint32_t bit = w * c, limb = bit >> 5, off = bit & 31;
+        uint64_t v = canon.l[limb];
+        if (limb + 1 < 8) v |= (uint64_t)canon.l[limb + 1] << 32;
+        uint32_t raw = ((uint32_t)(v >> off) & mask) + carry;
+        uint32_t sign = 0;
+        carry = 0;
+        if (w + 1 < W && raw > half) {
+            raw = (1u << c) - raw;
+            sign = 1;
+            carry = 1;
+        }
+        if (raw) f(w, raw, sign);
+    }
+}
+
+__global__ void __launch_bounds__(256) msm_count_kernel(const uint64_t *scalars, MsmCfg cfg, uint32_t *count) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cfg.n; i += (size_t)gridDim.x * blockDim.x) {
+        Fr s = load_fr(scalars, i).from_mont();
+        for_each_digit(s, cfg.c, cfg.W, [&](uint32_t w, uint32_t mag, uint32_t) {
+            atomicAdd(&count[(w << cfg.nb_log) + mag - 1], 1u);
+        });
+    }
+}
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const uint64_t *scalars, MsmCfg cfg, uint32_t *cursor, uint2 *entries) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cfg.n; i += (size_t)gridDim.x * blockDim.x) {
+        Fr s = load_fr(scalars, i).from_mont();
+        for_each_digit(s, cfg.c, cfg.W, [&](uint32_t w, uint32_t mag, uint32_t sign) {
+            const uint32_t gb = (w << cfg.nb_log) + mag - 1;
+            const uint32_t pos = atomicAdd(&cursor[gb], 1u);
+            entries[pos] = make_uint2(gb, (uint32_t)i | (sign << 31));
+        });
+    }
+}
+
+// ------------------------------------------------------------------------------------------- scan
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *block_total) {
+    __shared__ uint32_t warp_sums[32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t ws = warp_sums[lane];
+        uint32_t winc = ws;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= (uint32_t)o) winc += t;
+        }
+        warp_sums[lane] = winc - ws;  // exclusive
+        if (lane == 31 && block_total) *block_total = winc;
+    }
+    __syncthreads();
+    uint32_t r = inc - v + warp_sums[warp];
+    __syncthreads();
+    return r;
+}
+__global__ void __launch_bounds__(kScanThreads) scan_block_sums_kernel(const uint32_t *in, uint32_t n, uint32_t *block_sums) {
+    __shared__ uint32_t total;
+    const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    uint32_t s = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kScanItems; k++)
+        if (base + k < n) s += in[base + k];
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(kScanThreads) scan_top_kernel(uint32_t *block_sums, uint32_t nblocks, uint32_t *total_out) {
+    __shared__ uint32_t total;
+    const uint32_t per = (nblocks + kScanThreads - 1) / kScanThreads;
+    const uint32_t lo = threadIdx.x * per, hi = min(lo + per, nblocks);
+    uint32_t s = 0;
+    for (uint32_t i = lo; i < hi; i++) s += block_sums[i];
+    uint32_t ex = block_exclusive_scan(s, &total);
+    for (uint32_t i = lo; i < hi; i++) {
+        uint32_t v = block_sums[i];
+        block_sums[i] = ex;
+        ex += v;
+    }
+    if (threadIdx.x == 0) *total_out = total;
+}
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t *in, uint32_t n, const uint32_t *block_sums, uint32_t *out) {
+    const uint32_t base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    uint32_t v[kScanItems], s = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < kScanItems; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        s += v[k];
+    }
+    uint32_t ex = block_exclusive_scan(s, nullptr) + block_sums[blockIdx.x];
+#pragma unroll
+    for (uint32_t k = 0; k < kScanItems; k++) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------ accumulate
+// Output rule shared by every level.  A run that lies strictly inside its segment is complete and
+// goes to its bucket.  A run that touches the left (right) segment boundary *and* continues in the
+// neighbouring segment is a partial: left-touching partials go to the head slot, right-touching
+// ones to the tail slot; a run touching both sides stores its sum in the head slot and the identity
+// in the tail slot, so all partials of one bucket stay contiguous in slot order (no holes inside).
+struct RunSink {
+    G1Xyzz *buckets;
+    uint32_t *out_gb;
+    G1Xyzz *out_pt;
+    uint32_t t;
+    uint32_t head_gb, tail_gb;
+    __device__ __forceinline__ void flush(uint32_t gb, const G1Xyzz &acc, bool tl, bool tr) {
+        if (!tl && !tr) {
+            store_xyzz(buckets + gb, acc);
+        } else if (tl) {
+            head_gb = gb;
+            store_xyzz(out_pt + 2 * (size_t)t, acc);
+            if (tr) {
+                tail_gb = gb;
+                store_xyzz(out_pt + 2 * (size_t)t + 1, G1Xyzz::identity());
+            }
+        } else {
+            tail_gb = gb;
+            store_xyzz(out_pt + 2 * (size_t)t + 1, acc);
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        out_gb[2 * (size_t)t] = head_gb;
+        out_gb[2 * (size_t)t + 1] = tail_gb;
+    }
+};
+
+// Level 1: entries (bucket id, point index | sign) → buckets / partial slots, mixed additions.
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine *__restrict__ bases, const uint2 *__restrict__ entries,
+                                                             const uint32_t *__restrict__ n_entries_ptr, uint32_t L,
+                                                             G1Xyzz *buckets, uint32_t *out_gb, G1Xyzz *out_pt,
+                                                             uint32_t *n_out_ptr) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t M = *n_entries_ptr;
+    if (t == 0) *n_out_ptr = 2 * ((M + L - 1) / L);
+    const uint64_t start64 = (uint64_t)t * L;
+    if (start64 >= M) return;
+    const uint32_t start = (uint32_t)start64, end = (uint32_t)min((uint64_t)M, start64 + L);
+    const uint32_t prev = start > 0 ? entries[start - 1].x : kInvalid;
+    const uint32_t next = end < M ? entries[end].x : kInvalid;
+    RunSink sink{buckets, out_gb, out_pt, t, kInvalid, kInvalid};
+
+    uint2 e = entries[start];
+    uint32_t cur = e.x;
+    bool tl = (prev == cur);
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t i = start; i < end; i++) {
+        G1Affine pt = load_affine(bases, e.y);
+        const uint32_t gb = e.x;
+        if (i + 1 < end) {
+            e = entries[i + 1];
+            // pull the next base towards L2/L1 while this addition runs
+            const char *np = reinterpret_cast<const char *>(bases + (e.y & 0x7fffffffu));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(np));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(np + 64));
+        }
+        if (gb != cur) {
+            sink.flush(cur, acc, tl, false);
+            cur = gb;
+            tl = false;
+            acc = G1Xyzz::identity();
+        }
+        g1_madd(acc, pt);
+    }
+    sink.flush(cur, acc, tl, next == cur);
+    sink.finish();
+}
+// Levels ≥ 2: partial slots (bucket id or kInvalid, XYZZ point) → buckets / next-level slots.
+__global__ void __launch_bounds__(128) msm_accumulate_slots_kernel(const uint32_t *__restrict__ in_gb, const G1Xyzz *__restrict__ in_pt,
+                                                                   const uint32_t *__restrict__ n_in_ptr, uint32_t L,
+                                                                   G1Xyzz *buckets, uint32_t *out_gb, G1Xyzz *out_pt,
+                                                                   uint32_t *n_out_ptr) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_in = *n_in_ptr;
+    if (t == 0) *n_out_ptr = 2 * (uint32_t)(((uint64_t)n_in + L - 1) / L);
+    const uint64_t start64 = (uint64_t)t * L;
+    if (start64 >= n_in) return;
+    const uint32_t start = (uint32_t)start64, end = (uint32_t)min((uint64_t)n_in, start64 + L);
+    const uint32_t prev = start > 0 ? in_gb[start - 1] : kInvalid;
+    const uint32_t next = end < n_in ? in_gb[end] : kInvalid;
+    RunSink sink{buckets, out_gb, out_pt, t, kInvalid, kInvalid};
+
+    uint32_t cur = kInvalid;
+    bool have = false, tl = false;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t i = start; i < end; i++) {
+        const uint32_t gb = in_gb[i];
+        if (have && gb != cur) {  // a different bucket or a hole ends the run
+            sink.flush(cur, acc, tl, false);
+            have = false;
+        }
+        if (gb == kInvalid) continue;
+        if (!have) {
+            have = true;
+            cur = gb;
+            tl = (i == start && prev == gb);
+            acc = G1Xyzz::identity();
+        }
+        acc = g1_add(acc, load_xyzz(in_pt + i));
+    }
+    if (have) sink.flush(cur, acc, tl, next == cur);
+    sink.finish();
+}
+
+// ---------------------------------------------------------------------------------------- reduce
+// One thread per chunk of K consecutive buckets of one window:
+//   Σ_{j<K} (qK + j + 1)·B_{qK+j} = Σ_j (j+1)·B_j  (running sum)  +  (qK)·Σ_j B_j  (small scalar mul)
+__global__ void __launch_bounds__(128) msm_reduce_chunks_kernel(const G1Xyzz *__restrict__ buckets, const uint32_t *__restrict__ count,
+                                                                MsmCfg cfg, G1Xyzz *chunk_sums) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t chunks_log = cfg.nb_log - cfg.K_log;
+    if (t >= (cfg.W << chunks_log)) return;
+    const uint32_t w = t >> chunks_log, q = t & ((1u << chunks_log) - 1), K = 1u << cfg.K_log;
+    const uint32_t base = (w << cfg.nb_log) + (q << cfg.K_log);
+    G1Xyzz run = G1Xyzz::identity(), acc = G1Xyzz::identity();
+    for (int j = (int)K - 1; j >= 0; j--) {
+        if (count[base + j]) run = g1_add(run, load_xyzz(buckets + base + j));
+        acc = g1_add(acc, run);
+    }
+    if (q) acc = g1_add(acc, g1_mul_small(run, (uint64_t)q << cfg.K_log));
+    store_xyzz(chunk_sums + t, acc);
+}
+// One CTA per window: tree sum of its chunk sums.
+__global__ void __launch_bounds__(128) msm_window_sum_kernel(const G1Xyzz *__restrict__ chunk_sums, uint32_t chunks_per_window,
+                                                             G1Xyzz *window_sums) {
+    __shared__ uint4 sm[128 * 12];
+    const uint32_t w = blockIdx.x, tid = threadIdx.x;
+    G1Xyzz acc = G1Xyzz::identity();
+    for (uint32_t i = tid; i < chunks_per_window; i += blockDim.x)
+        acc = g1_add(acc, load_xyzz(chunk_sums + (size_t)w * chunks_per_window + i));
+    G1Xyzz *smp = reinterpret_cast<G1Xyzz *>(sm);
+    store_xyzz(smp + tid, acc);
+    __syncthreads();
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (tid < s) {
+            acc = g1_add(load_xyzz(smp + tid), load_xyzz(smp + tid + s));
+            store_xyzz(smp + tid, acc);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) store_xyzz(window_sums + w, acc);
+}
+// Horner over the windows, optional accumulation across pieces, normalisation to affine.
+// result: 36 words — x[12] ‖ y[12] ‖ z[12] with z = R (finite) or (0, R, 0) for the identity.
+__global__ void msm_combine_kernel(const G1Xyzz *window_sums, MsmCfg cfg, G1Xyzz *running_total, int first_piece,
+                                   int last_piece, uint32_t *result) {
+    G1Xyzz total = G1Xyzz::identity();
+    for (int w = (int)cfg.W - 1; w >= 0; w--) {
+        for (uint32_t k = 0; k < cfg.c; k++) total = g1_dbl(total);
+        total = g1_add(total, load_xyzz(window_sums + w));
+    }
+    if (!first_piece) total = g1_add(total, load_xyzz(running_total));
+    store_xyzz(running_total, total);
+    if (last_piece) {
+        G1Affine a;
+        Fp z = Fp::one();
+        if (!g1_to_affine(total, a)) {
+            a.x = Fp::zero();
+            a.y = Fp::one();
+            z = Fp::zero();
+        }
+        for (int i = 0; i < 12; i++) {
+            result[i] = a.x.l[i];
+            result[12 + i] = a.y.l[i];
+            result[24 + i] = z.l[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ synthetic bases
+// bases[i] = (a + i·d)·G; each thread walks `per` consecutive points by repeated addition of d·G.
+__global__ void __launch_bounds__(128) synthetic_bases_kernel(G1Affine *out, uint64_t n, uint64_t a, uint64_t d, uint32_t per) {
+    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const uint64_t i0 = t * per;
+    if (i0 >= n) return;
+    // G1 generator, Montgomery form
+    G1Affine g;
+    {
+        const uint32_t gx[12] = {0xfd530c16u, 0x5cb38790u, 0x9976fff5u, 0x7817fc67u, 0x143ba1c1u, 0x154f95c7u,
+                                 0xf3d0e747u, 0xf0ae6acdu, 0x21dbf440u, 0xedce6eccu, 0x9e0bfb75u, 0x12017741u};
+        const uint32_t gy[12] = {0x0ce72271u, 0xbaac93d5u, 0x7918fd8eu, 0x8c22631au, 0x570725ceu, 0xdd595f13u,
+                                 0x50405194u, 0x51ac5829u, 0xad0059c0u, 0x0e1c8c3fu, 0x5008a26au, 0x0bbc3efcu};
+        for (int k = 0; k < 12; k++) { g.x.l[k] = gx[k]; g.y.l[k] = gy[k]; }
+    }
+    const G1Xyzz G = G1Xyzz::from_affine(g);
+    G1Xyzz cur = g1_mul_small(G, a + i0 * d);
+    const G1Xyzz step = g1_mul_small(G, d);
+    for (uint32_t k = 0; k < per && i0 + k < n; k++) {
+        G1Affine af;
+        g1_to_affine(cur, af);  // (a + i·d) is never ≡ 0 mod r for the sizes used
+        store_fp2(reinterpret_cast<uint4 *>(out + i0 + k), af.x, af.y);
+        cur = g1_add(cur, step);
+    }
+}
+
+// Window width minimising W·(n + 3·2^(c−1)): n·W mixed additions plus ≈ 3 addition-equivalents per bucket
+// for the running-sum reduction.
+uint32_t choose_window(size_t n) {
+    uint32_t best_c = 4;
+    double best = 1e300;
+    for (uint32_t c = 4; c <= 23; c++) {
+        const double W = (256 + c - 1) / c;
+        const double cost = W * ((double)n + 3.0 * (double)(1u << (c - 1)));
+        if (cost <= best) { best = cost; best_c = c; }
+    }
+    return best_c;
+}
+uint32_t floor_pow2(uint64_t v) {
+    uint32_t p = 1;
+    while (((uint64_t)p << 1) <= v) p <<= 1;
+    return p;
+}
+
+}  // namespace
+
 int msm_module_init(pb200_ctx *) { return 0; }
-extern "C" int pb200_srs_upload(pb200_ctx *ctx, const uint64_t *, size_t, pb200_srs **) { return pb_fail(ctx, PB200_ERR_ARG, "msm", "not built yet", __FILE__, __LINE__); }
-extern "C" int pb200_srs_wrap_dev(pb200_ctx *ctx, const uint64_t *, size_t, pb200_srs **) { return pb_fail(ctx, PB200_ERR_ARG, "msm", "not built yet", __FILE__, __LINE__); }
-extern "C" void pb200_srs_free(pb200_ctx *, pb200_srs *) {}
-extern "C" size_t pb200_srs_len(const pb200_srs *) { return 0; }
-extern "C" int pb200_msm_g1(pb200_ctx *ctx, const pb200_srs *, size_t, const uint64_t *, size_t, uint64_t *) { return pb_fail(ctx, PB200_ERR_ARG, "msm", "not built yet", __FILE__, __LINE__); }
-extern "C" int pb200_msm_g1_dev(pb200_ctx *ctx, const pb200_srs *, size_t, const uint64_t *, size_t, uint64_t *) { return pb_fail(ctx, PB200_ERR_ARG, "msm", "not built yet", __FILE__, __LINE__); }
-extern "C" uint32_t pb200_msm_window_bits(size_t) { return 0; }
-extern "C" int pb200_synthetic_bases_dev(pb200_ctx *ctx, uint64_t *, size_t, uint64_t, uint64_t) { return pb_fail(ctx, PB200_ERR_ARG, "msm", "not built yet", __FILE__, __LINE__); }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// One piece (n < 2^27) of an MSM; bases / scalars on the device.
+static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scalars, uint32_t n, int first, int last,
+                     G1Xyzz *running_total, uint32_t *result_dev) {
+    MsmCfg cfg;
+    cfg.n = n;
+    cfg.c = choose_window(n);
+    cfg.W = (256 + cfg.c - 1) / cfg.c;
+    cfg.nb_log = cfg.c - 1;
+    const uint64_t m0 = (uint64_t)n * cfg.W;  // upper bound on entries
+    PB_ARG(ctx, m0 < (1ull << 32));
+    cfg.L1 = std::min<uint32_t>(128, std::max<uint32_t>(8, floor_pow2(m0 / 262144 + 1)));
+    cfg.L2 = 16;
+    const uint32_t TB = cfg.W << cfg.nb_log;  // total buckets
+    {   // chunk size for the bucket reduction: aim for ≥ 64 Ki chunk threads, 8 ≤ K ≤ 256
+        uint32_t k_log = 3;
+        while (k_log < 8 && (TB >> (k_log + 1)) >= 65536) k_log++;
+        cfg.K_log = std::min(k_log, cfg.nb_log);
+    }
+    const uint32_t n_chunks = TB >> cfg.K_log, chunks_per_window = n_chunks / cfg.W;
+
+    // level bounds
+    std::vector<uint32_t> lvl_threads, lvl_slots;
+    lvl_threads.push_back((uint32_t)((m0 + cfg.L1 - 1) / cfg.L1));
+    lvl_slots.push_back(2 * lvl_threads[0]);
+    while (lvl_slots.back() > 32) {
+        uint32_t thr = (lvl_slots.back() + cfg.L2 - 1) / cfg.L2;
+        lvl_threads.push_back(thr);
+        lvl_slots.push_back(2 * thr);
+    }
+    const uint32_t n_scan_blocks = (TB + kScanTile - 1) / kScanTile;
+
+    // workspace carve-up
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    const size_t o_count = carve((size_t)TB * 4), o_cursor = carve((size_t)TB * 4), o_bsum = carve((size_t)n_scan_blocks * 4);
+    const size_t o_meta = carve(64 * 4);
+    const size_t o_entries = carve((size_t)m0 * 8);
+    const size_t o_buckets = carve((size_t)TB * sizeof(G1Xyzz));
+    const size_t slotsA = lvl_slots[0], slotsB = lvl_slots.size() > 1 ? lvl_slots[1] : 2;
+    const size_t o_gbA = carve(slotsA * 4), o_ptA = carve(slotsA * sizeof(G1Xyzz));
+    const size_t o_gbB = carve(slotsB * 4), o_ptB = carve(slotsB * sizeof(G1Xyzz));
+    const size_t o_chunks = carve((size_t)n_chunks * sizeof(G1Xyzz)), o_wsum = carve((size_t)cfg.W * sizeof(G1Xyzz));
+    PB_TRY(pb_ensure(ctx, &ctx->msm_ws, &ctx->msm_ws_bytes, off));
+    char *ws = (char *)ctx->msm_ws;
+    uint32_t *count = (uint32_t *)(ws + o_count), *cursor = (uint32_t *)(ws + o_cursor), *bsum = (uint32_t *)(ws + o_bsum);
+    uint32_t *meta = (uint32_t *)(ws + o_meta);  // [0] = #entries, [1+k] = #slots produced by level k
+    uint2 *entries = (uint2 *)(ws + o_entries);
+    G1Xyzz *buckets = (G1Xyzz *)(ws + o_buckets);
+    uint32_t *gbA = (uint32_t *)(ws + o_gbA), *gbB = (uint32_t *)(ws + o_gbB);
+    G1Xyzz *ptA = (G1Xyzz *)(ws + o_ptA), *ptB = (G1Xyzz *)(ws + o_ptB);
+    G1Xyzz *chunks = (G1Xyzz *)(ws + o_chunks), *wsum = (G1Xyzz *)(ws + o_wsum);
+    cudaStream_t st = ctx->stream;
+
+    PbTimer t_sort(ctx, "msm.sort");
+    PB_CUDA(ctx, cudaMemsetAsync(count, 0, (size_t)TB * 4, st));
+    const uint32_t sgrid = std::min<uint32_t>((n + 255) / 256, ctx->sm_count * 16);
+    msm_count_kernel<<<sgrid, 256, 0, st>>>(scalars, cfg, count);
+    PB_LAUNCHED(ctx);
+    scan_block_sums_kernel<<<n_scan_blocks, kScanThreads, 0, st>>>(count, TB, bsum);
+    PB_LAUNCHED(ctx);
+    scan_top_kernel<<<1, kScanThreads, 0, st>>>(bsum, n_scan_blocks, meta + 0);
+    PB_LAUNCHED(ctx);
+    scan_apply_kernel<<<n_scan_blocks, kScanThreads, 0, st>>>(count, TB, bsum, cursor);
+    PB_LAUNCHED(ctx);
+    msm_scatter_kernel<<<sgrid, 256, 0, st>>>(scalars, cfg, cursor, entries);
+    PB_LAUNCHED(ctx);
+    t_sort.stop();
+
+    PbTimer t_acc(ctx, "msm.accumulate");
+    msm_accumulate_kernel<<<(lvl_threads[0] + 127) / 128, 128, 0, st>>>(bases, entries, meta + 0, cfg.L1, buckets, gbA, ptA, meta + 1);
+    PB_LAUNCHED(ctx);
+    t_acc.stop();
+    PbTimer t_fix(ctx, "msm.partials");
+    {
+        uint32_t *in_gb = gbA, *out_gb = gbB;
+        G1Xyzz *in_pt = ptA, *out_pt = ptB;
+        for (size_t k = 1; k < lvl_threads.size(); k++) {
+            msm_accumulate_slots_kernel<<<(lvl_threads[k] + 127) / 128, 128, 0, st>>>(in_gb, in_pt, meta + k, cfg.L2, buckets, out_gb,
+                                                                                      out_pt, meta + k + 1);
+            PB_LAUNCHED(ctx);
+            std::swap(in_gb, out_gb);
+            std::swap(in_pt, out_pt);
+        }
+        // whatever is left (≤ 32 slots) is finished by one thread: no neighbours, so every run is complete
+        msm_accumulate_slots_kernel<<<1, 1, 0, st>>>(in_gb, in_pt, meta + lvl_threads.size(), 0x7fffffffu, buckets, out_gb, out_pt,
+                                                      meta + lvl_threads.size() + 1);
+        PB_LAUNCHED(ctx);
+    }
+    t_fix.stop();
+
+    PbTimer t_red(ctx, "msm.reduce");
+    msm_reduce_chunks_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(buckets, count, cfg, chunks);
+    PB_LAUNCHED(ctx);
+    msm_window_sum_kernel<<<cfg.W, 128, 0, st>>>(chunks, chunks_per_window, wsum);
+    PB_LAUNCHED(ctx);
+    msm_combine_kernel<<<1, 1, 0, st>>>(wsum, cfg, running_total, first, last, result_dev);
+    PB_LAUNCHED(ctx);
+    t_red.stop();
+    if (ctx->profile) {
+        PB_CUDA(ctx, cudaStreamSynchronize(st));
+        t_sort.collect();
+        t_acc.collect();
+        t_fix.collect();
+        t_red.collect();
+    }
+    return 0;
+}
+
+static int msm_run(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_dev, size_t n, uint64_t *out_host) {
+    // identity for the empty sum
+    if (n == 0) {
+        memset(out_host, 0, 18 * 8);
+        const uint64_t r1[6] = {0x760900000002fffdull, 0xebf4000bc40c0002ull, 0x5f48985753c758baull,
+                                0x77ce585370525745ull, 0x5c071a97a256ec6dull, 0x15f65ec3fa80e493ull};
+        memcpy(out_host + 6, r1, 48);
+        return 0;
+    }
+    PB_ARG(ctx, srs != nullptr && srs->dev != nullptr);
+    PB_ARG(ctx, offset <= srs->n && n <= srs->n - offset);
+    PB_ARG(ctx, scalars_dev != nullptr);
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const G1Affine *bases = reinterpret_cast<const G1Affine *>(srs->dev) + offset;
+    void *small = nullptr;  // running total (XYZZ) + result (36 words)
+    PB_CUDA(ctx, cudaMallocAsync(&small, sizeof(G1Xyzz) + 36 * 4, ctx->stream));
+    G1Xyzz *running = (G1Xyzz *)small;
+    uint32_t *result = (uint32_t *)((char *)small + sizeof(G1Xyzz));
+    PbTimer t_total(ctx, "msm.total");
+    const size_t piece = (size_t)1 << 26;
+    int rc = 0;
+    for (size_t done = 0; done < n && rc == 0; done += piece) {
+        const uint32_t m = (uint32_t)std::min(piece, n - done);
+        rc = msm_piece(ctx, bases + done, scalars_dev + 4 * done, m, done == 0, done + m == n, running, result);
+    }
+    t_total.stop();
+    cudaError_t e = cudaSuccess;
+    if (rc == 0) e = cudaMemcpyAsync(ctx->pinned, result, 36 * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFreeAsync(small, ctx->stream);
+    if (rc) return rc;
+    if (e != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "msm result copy", cudaGetErrorString(e), __FILE__, __LINE__);
+    if (e2 != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "msm sync", cudaGetErrorString(e2), __FILE__, __LINE__);
+    t_total.collect();
+    memcpy(out_host, ctx->pinned, 36 * 4);
+    return 0;
+}
+
+extern "C" int pb200_srs_upload(pb200_ctx *ctx, const uint64_t *xy_mont_host, size_t n_points, pb200_srs **out) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, out != nullptr && (xy_mont_host != nullptr || n_points == 0));
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *dev = nullptr;
+    PB_CUDA(ctx, cudaMalloc(&dev, std::max<size_t>(n_points, 1) * 96));
+    if (n_points) {
+        cudaError_t e = cudaMemcpyAsync(dev, xy_mont_host, n_points * 96, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            cudaFree(dev);
+            return pb_fail(ctx, PB200_ERR_CUDA, "srs upload", cudaGetErrorString(e), __FILE__, __LINE__);
+        }
+    }
+    pb200_srs *s = new pb200_srs();
+    s->dev = (const uint64_t *)dev;
+    s->n = n_points;
+    s->owned = true;
+    *out = s;
+    return 0;
+}
+extern "C" int pb200_srs_wrap_dev(pb200_ctx *ctx, const uint64_t *xy_mont_dev, size_t n_points, pb200_srs **out) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, out != nullptr && xy_mont_dev != nullptr);
+    pb200_srs *s = new pb200_srs();
+    s->dev = xy_mont_dev;
+    s->n = n_points;
+    s->owned = false;
+    *out = s;
+    return 0;
+}
+extern "C" void pb200_srs_free(pb200_ctx *ctx, pb200_srs *srs) {
+    if (!srs) return;
+    if (srs->owned && srs->dev) {
+        if (ctx) cudaStreamSynchronize(ctx->stream);
+        cudaFree((void *)srs->dev);
+    }
+    delete srs;
+}
+extern "C" size_t pb200_srs_len(const pb200_srs *srs) { return srs ? srs->n : 0; }
+extern "C" uint32_t pb200_msm_window_bits(size_t n) { return choose_window(std::min<size_t>(n, (size_t)1 << 26)); }
+
+extern "C" int pb200_msm_g1_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_mont_dev, size_t n,
+                                uint64_t out_xyz_mont[18]) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, out_xyz_mont != nullptr);
+    return msm_run(ctx, srs, offset, scalars_mont_dev, n, out_xyz_mont);
+}
+extern "C" int pb200_msm_g1(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_mont_host, size_t n,
+                            uint64_t out_xyz_mont[18]) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, out_xyz_mont != nullptr);
+    if (n == 0) return msm_run(ctx, srs, offset, nullptr, 0, out_xyz_mont);
+    PB_ARG(ctx, scalars_mont_host != nullptr);
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *dev = nullptr;
+    PB_CUDA(ctx, cudaMallocAsync(&dev, n * 32, ctx->stream));
+    cudaError_t e = cudaMemcpyAsync(dev, scalars_mont_host, n * 32, cudaMemcpyHostToDevice, ctx->stream);
+    int rc = 0;
+    if (e == cudaSuccess) rc = msm_run(ctx, srs, offset, (const uint64_t *)dev, n, out_xyz_mont);
+    cudaFreeAsync(dev, ctx->stream);
+    if (e != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "scalar upload", cudaGetErrorString(e), __FILE__, __LINE__);
+    return rc;
+}
+extern "C" int pb200_synthetic_bases_dev(pb200_ctx *ctx, uint64_t *xy_mont_dev, size_t n, uint64_t a, uint64_t d) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, xy_mont_dev != nullptr || n == 0);
+    if (n == 0) return 0;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t per = 32;
+    const uint64_t threads = (n + per - 1) / per;
+    synthetic_bases_kernel<<<(uint32_t)((threads + 127) / 128), 128, 0, ctx->stream>>>((G1Affine *)xy_mont_dev, n, a, d, per);
+    PB_LAUNCHED(ctx);
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}

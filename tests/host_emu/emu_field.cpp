@@ -26,3 +26,42 @@ extern "C" {
 void emu_fr(int op, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n) { binop<Fr>(op, a, b, o, n); }
 void emu_fp(int op, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n) { binop<Fp>(op, a, b, o, n); }
 }
+
+// ---- G1 (csrc/g1.cuh) -------------------------------------------------------------------------------
+#include "../../plonk-prototype_b200/csrc/g1.cuh"
+static G1Affine ld_aff(const uint32_t *p) { G1Affine a; memcpy(a.x.l, p, 48); memcpy(a.y.l, p + 12, 48); return a; }
+static void st_xyzz_affine(const G1Xyzz &v, uint32_t *o) {  // o: 24 words x‖y, then 1 word "is identity"
+    G1Affine a;
+    if (!g1_to_affine(v, a)) { memset(o, 0, 96); o[24] = 1; return; }
+    memcpy(o, a.x.l, 48); memcpy(o + 12, a.y.l, 48); o[24] = 0;
+}
+extern "C" {
+// op 0: P+Q via madd; 1: P+Q via add (both XYZZ, second one re-randomised by doubling twice and adding back);
+// 2: 2P via dbl_affine; 3: 2P via dbl on XYZZ; 4: k·P small; 5: chain: ((P+Q)+Q)+(−Q) via madd;
+// inputs are packed affine Montgomery (24 words each); output 25 words per element.
+void emu_g1(int op, const uint32_t *p, const uint32_t *q, uint32_t *o, size_t n, uint64_t k) {
+    for (size_t i = 0; i < n; i++) {
+        G1Affine P = ld_aff(p + 24 * i), Q = ld_aff(q + 24 * i);
+        G1Xyzz r;
+        switch (op) {
+            case 0: r = G1Xyzz::from_affine(P); g1_madd(r, Q); break;
+            case 1: {
+                G1Xyzz a = g1_dbl(g1_dbl_affine(P));           // 4P in non-trivial ZZ
+                G1Xyzz nP = G1Xyzz::from_affine(P); nP.y = nP.y.neg();
+                a = g1_add(a, nP); a = g1_add(a, nP); a = g1_add(a, nP);  // back to P with ZZ ≠ 1
+                G1Xyzz b = g1_dbl_affine(Q); G1Xyzz nQ = G1Xyzz::from_affine(Q); nQ.y = nQ.y.neg();
+                b = g1_add(b, nQ);                             // Q with ZZ ≠ 1
+                r = g1_add(a, b);
+                break;
+            }
+            case 2: r = g1_dbl_affine(P); break;
+            case 3: r = g1_dbl(g1_dbl_affine(P)); break;
+            case 4: r = g1_mul_small(G1Xyzz::from_affine(P), k); break;
+            case 5: { r = G1Xyzz::from_affine(P); g1_madd(r, Q); g1_madd(r, Q); G1Affine nQ = Q; nQ.y = nQ.y.neg(); g1_madd(r, nQ); break; }
+            case 6: { r = G1Xyzz::identity(); g1_madd(r, P); G1Affine nP = P; nP.y = nP.y.neg(); g1_madd(r, nP); g1_madd(r, Q); break; }
+            default: r = G1Xyzz::identity();
+        }
+        st_xyzz_affine(r, o + 25 * i);
+    }
+}
+}

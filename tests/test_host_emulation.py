@@ -71,3 +71,49 @@ def test_fp_matches_oracle(emu, oracle):
     assert (_run(emu, "emu_fp", 3, a, b) == oracle.fp_from_mont(a)).all()
     assert (_run(emu, "emu_fp", 4, a, b) == oracle.fp_to_mont(a)).all()
     assert (_run(emu, "emu_fp", 5, a[:32], b[:32]) == oracle.fp_inv(a[:32])).all()
+
+
+def _g1(lib, op, P, Q, k=0):
+    P32 = np.ascontiguousarray(P).view(np.uint32).reshape(-1, 24)
+    Q32 = np.ascontiguousarray(Q).view(np.uint32).reshape(-1, 24)
+    o = np.zeros((P32.shape[0], 25), np.uint32)
+    lib.emu_g1(op, P32.ctypes.data_as(ctypes.c_void_p), Q32.ctypes.data_as(ctypes.c_void_p),
+               o.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(P32.shape[0]), ctypes.c_uint64(k))
+    return o
+
+
+def _affine_ints(oracle, o):
+    """emu output rows → list of canonical affine (x, y) or None."""
+    res = []
+    for row in o:
+        if row[24]:
+            res.append(None)
+            continue
+        xy = oracle.fp_from_mont(row[:24].copy().view(np.uint64).reshape(2, 6))
+        res.append((oracle.limbs_to_int(xy[0]), oracle.limbs_to_int(xy[1])))
+    return res
+
+
+def test_g1_group_law_matches_model(emu, oracle):
+    n = 24
+    pts = oracle.synthetic_bases(2 * n)
+    P, Q = pts[:n].copy(), pts[n:].copy()
+    Q[0] = P[0]                                   # P + P  → doubling branch
+    zero = np.zeros((1, 6), np.uint64)
+    Q[1, :6] = P[1, :6]
+    Q[1, 6:] = oracle.fp_sub(zero, P[1:2, 6:])    # P + (−P) → identity branch
+    mp = model.synthetic_bases(2 * n)
+    MP, MQ = mp[:n], mp[n:]
+    MQ[0] = MP[0]
+    MQ[1] = model.g1_neg(MP[1])
+    want_add = [model.g1_add(a, b) for a, b in zip(MP, MQ)]
+    assert _affine_ints(oracle, _g1(emu, 0, P, Q)) == want_add        # mixed add incl. exceptional cases
+    assert _affine_ints(oracle, _g1(emu, 1, P, Q)) == want_add        # general add incl. exceptional cases
+    want_dbl = [model.g1_add(a, a) for a in MP]
+    assert _affine_ints(oracle, _g1(emu, 2, P, Q)) == want_dbl
+    assert _affine_ints(oracle, _g1(emu, 3, P, Q)) == [model.g1_add(d, d) for d in want_dbl]
+    for k in (0, 1, 2, 3, 0xB2, 2**21 - 1, 2**40 + 12345):
+        assert _affine_ints(oracle, _g1(emu, 4, P[:6], Q[:6], k)) == [model.g1_mul(a, k) for a in MP[:6]]
+    assert _affine_ints(oracle, _g1(emu, 5, P, Q)) == [model.g1_add(model.g1_add(model.g1_add(a, b), b), model.g1_neg(b))
+                                                        for a, b in zip(MP, MQ)]
+    assert _affine_ints(oracle, _g1(emu, 6, P, Q)) == MQ              # identity accumulator paths

@@ -1,0 +1,150 @@
+"""GPU parity tests for the MSM path, through the C ABI (pb200_msm_g1 / pb200_msm_g1_dev) and the
+msm_variable_base / CommitKey mirrors, against (a) the big-int golden vectors, (b) the C oracle's
+restatement of msm_variable_base on seeded inputs, (c) closed-form and linearity properties at sizes the
+oracle cannot reach.  Results are compared as canonical affine points — bit-exact, no tolerance."""
+import numpy as np
+import pytest
+
+import model
+from helpers import closed_form_msm_scalar, load_golden
+from test_oracle_cpu import expected_affine, msm_case_inputs
+
+pytestmark = pytest.mark.gpu
+A, D = 0xB2000001, 0x9E3779B1
+
+
+def aff(oracle, xyz):
+    return oracle.g1_proj_to_affine_canonical(xyz)
+
+
+def test_golden_vectors(ctx, oracle):
+    import plonk_prototype_b200 as pb
+    for case in load_golden("msm_kat.json")["cases"]:
+        pts, s = msm_case_inputs(oracle, case)
+        out = pb.msm_variable_base(pts, s, ctx)
+        got = aff(oracle, out)
+        assert got == expected_affine(case), case["name"]
+        assert model.g1_compress(got).hex() == case["compressed"]
+        # result convention: Z = R for finite points, (0, R, 0) for the identity
+        r1 = oracle.fp_consts()["r1"]
+        if got is None:
+            assert not out[:6].any() and (out[6:12] == r1).all() and not out[12:].any()
+        else:
+            assert (out[12:] == r1).all()
+
+
+def test_empty_input_is_identity(ctx, oracle):
+    import plonk_prototype_b200 as pb
+    out = pb.msm_variable_base(np.zeros((0, 12), np.uint64), np.zeros((0, 4), np.uint64), ctx)
+    assert aff(oracle, out) is None
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 100, 257, 1000, 4096, 1 << 14, 1 << 16])
+def test_random_matches_oracle(ctx, oracle, n):
+    pts = oracle.synthetic_bases(n)
+    s = oracle.fr_to_mont(oracle.random_fr(0xB2000000 + n, n))
+    import plonk_prototype_b200 as pb
+    got = aff(oracle, pb.msm_variable_base(pts, s, ctx))
+    want = aff(oracle, oracle.msm_variable_base(pts, s, threads=16))
+    assert got == want
+
+
+def test_adversarial_scalar_sets(ctx, oracle):
+    """SURVEY.md §8d adversarial sets: bucket skew and the exceptional cases of the group law."""
+    n = 1 << 13
+    pts = oracle.synthetic_bases(n)
+    ck_ctx = ctx
+    srs = ck_ctx.srs_upload(pts)
+    rnd = model.random_fr(0xADD, n)
+    sets = {
+        "all_zero": [0] * n,
+        "all_one": [1] * n,
+        "all_r_minus_1": [model.R - 1] * n,
+        "all_two": [2] * n,
+        "eight_bit": [v & 0xFF for v in rnd],
+        "half_zero": [0 if i & 1 else v for i, v in enumerate(rnd)],
+        "one_heavy_bucket": [0x1234 if i % 3 else v for i, v in enumerate(rnd)],
+        "top_window_only": [(v >> 240) << 240 for v in rnd],
+    }
+    try:
+        for name, vals in sets.items():
+            s = oracle.fr_to_mont(oracle.ints_to_limbs(vals, 4))
+            got = aff(oracle, ck_ctx.msm(srs, s))
+            want = aff(oracle, oracle.msm_variable_base(pts, s, threads=16))
+            assert got == want, name
+            k = closed_form_msm_scalar(s, A, D, model.R, model.FR_MONT_R)
+            assert got == model.g1_mul(model.G1_GEN, k), name
+    finally:
+        ck_ctx.srs_free(srs)
+
+
+def test_adversarial_base_sets(ctx, oracle):
+    import plonk_prototype_b200 as pb
+    n = 1 << 12
+    base = oracle.synthetic_bases(n)
+    s = oracle.fr_to_mont(oracle.random_fr(0xBA5E, n))
+    same = np.repeat(base[:1], n, axis=0)                              # all-equal bases → P + P everywhere
+    assert aff(oracle, pb.msm_variable_base(same, s, ctx)) == aff(oracle, oracle.msm_variable_base(same, s, threads=16))
+    half = base[: n // 2]
+    neg = half.copy()
+    neg[:, 6:] = oracle.fp_sub(np.zeros((n // 2, 6), np.uint64), half[:, 6:])
+    pm = np.ascontiguousarray(np.stack([half, neg], axis=1).reshape(n, 12))  # P, −P pairs
+    assert aff(oracle, pb.msm_variable_base(pm, s, ctx)) == aff(oracle, oracle.msm_variable_base(pm, s, threads=16))
+    s2 = np.repeat(s[: n // 2], 2, axis=0)                              # equal scalars on ±P → identity
+    assert aff(oracle, pb.msm_variable_base(pm, np.ascontiguousarray(s2), ctx)) is None
+
+
+def test_commit_key_prefix_and_offset(ctx, oracle):
+    """CommitKey::commit uses powers_of_g[..len]; the ABI's (offset, n) addresses any sub-range."""
+    import plonk_prototype_b200 as pb
+    n = 3000
+    pts = oracle.synthetic_bases(n)
+    ck = pb.CommitKey(pts, ctx)
+    s = oracle.fr_to_mont(oracle.random_fr(0xC0FFEE, 1234))
+    assert aff(oracle, ck.commit(s)) == aff(oracle, oracle.msm_variable_base(pts[:1234], s, threads=8))
+    got = aff(oracle, ctx.msm(ck._srs, s[:500], offset=2000))
+    assert got == aff(oracle, oracle.msm_variable_base(pts[2000:2500], s[:500], threads=8))
+    with pytest.raises(ValueError):
+        ck.commit(np.zeros((n + 1, 4), np.uint64))                     # PolynomialDegreeTooLarge
+    with pytest.raises(pb.Pb200Error):
+        ctx.msm(ck._srs, s, offset=n - 10)                             # range outside the SRS
+    ck.close()
+
+
+def test_synthetic_bases_on_device_match_oracle(ctx, oracle):
+    n = 5000
+    d = ctx.malloc(n * 96)
+    try:
+        ctx.synthetic_bases_dev(d, n, A, D)
+        got = np.empty((n, 12), np.uint64)
+        ctx.d2h(got, d)
+        assert (got == oracle.synthetic_bases(n, A, D)).all()
+    finally:
+        ctx.free(d)
+
+
+@pytest.mark.parametrize("log_n", [18, 20, 22])
+def test_closed_form_and_linearity_large(ctx, oracle, log_n):
+    """Device-resident bases + scalars; exact check of the whole MSM against (Σ sᵢ(a+i·d))·G."""
+    n = 1 << log_n
+    bases = ctx.malloc(n * 96)
+    sd = ctx.malloc(n * 32)
+    try:
+        ctx.synthetic_bases_dev(bases, n, A, D)
+        sample = np.empty((64, 12), np.uint64)
+        ctx.d2h(sample, bases + (n - 64) * 96)
+        assert oracle.g1_on_curve(sample)
+        srs = ctx.srs_wrap_dev(bases, n)
+        s = oracle.random_fr(0xB2000000 + log_n, n)      # raw limbs < r: valid Montgomery representations
+        t = oracle.random_fr(0xB2100000 + log_n, n)
+        res = {}
+        for name, v in (("s", s), ("t", t), ("s+t", oracle.fr_add(s, t))):
+            ctx.h2d(sd, v)
+            got = aff(oracle, ctx.msm_dev(srs, sd, n))
+            assert got == model.g1_mul(model.G1_GEN, closed_form_msm_scalar(v, A, D, model.R, model.FR_MONT_R)), name
+            res[name] = got
+        assert model.g1_add(res["s"], res["t"]) == res["s+t"]
+        ctx.srs_free(srs)
+    finally:
+        ctx.free(bases)
+        ctx.free(sd)
