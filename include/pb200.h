@@ -88,6 +88,10 @@ PB200_API int pb200_msm_g1(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, 
 /* Same with scalars already on the DEVICE (n × 32 B).  Blocks; result on the host. */
 PB200_API int pb200_msm_g1_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_mont_dev, size_t n,
                      uint64_t out_xyz_mont[18]);
+/* Sum of `count` projective points (each X ‖ Y ‖ Z, 18 × u64 Montgomery, HOST memory) — the combine step after
+ * a point-range-sharded MSM: every rank's partial result is gathered and added here.
+ * Output normalised like pb200_msm_g1's. */
+PB200_API int pb200_g1_sum(pb200_ctx *ctx, const uint64_t *points_xyz_mont_host, size_t count, uint64_t out_xyz_mont[18]);
 /* Pippenger window width used for n points (exposed for the benches' work model). */
 PB200_API uint32_t pb200_msm_window_bits(size_t n);
 

@@ -17,7 +17,7 @@ EXPORTS = [
     "pb200_malloc", "pb200_free", "pb200_h2d", "pb200_d2h",
     "pb200_domain_log_size", "pb200_ntt", "pb200_ntt_dev",
     "pb200_srs_upload", "pb200_srs_wrap_dev", "pb200_srs_free", "pb200_srs_len",
-    "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_window_bits",
+    "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_g1_sum", "pb200_msm_window_bits",
     "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_launch_count",
     "pb200_imad_peak",
 ]
@@ -58,6 +58,7 @@ def lib():
         L.pb200_srs_len.restype = ctypes.c_size_t
         L.pb200_msm_g1.argtypes = [vp, vp, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]
         L.pb200_msm_g1_dev.argtypes = [vp, vp, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]
+        L.pb200_g1_sum.argtypes = [vp, u64p, ctypes.c_size_t, u64p]
         L.pb200_msm_window_bits.argtypes = [ctypes.c_size_t]
         L.pb200_msm_window_bits.restype = ctypes.c_uint32
         L.pb200_synthetic_bases_dev.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64]
@@ -161,6 +162,12 @@ class Context:
     def msm_dev(self, srs, scalars_dev, n, offset=0):
         out = np.zeros(18, np.uint64)
         self._check(lib().pb200_msm_g1_dev(self._h, srs, offset, ctypes.c_void_p(scalars_dev), n, _ptr(out)))
+        return out
+
+    def g1_sum(self, points_xyz_host):
+        pts = np.ascontiguousarray(points_xyz_host, dtype=np.uint64).reshape(-1, 18)
+        out = np.zeros(18, np.uint64)
+        self._check(lib().pb200_g1_sum(self._h, _ptr(pts), pts.shape[0], _ptr(out)))
         return out
 
     def synthetic_bases_dev(self, dev, n, a=0xB2000001, d=0x9E3779B1):

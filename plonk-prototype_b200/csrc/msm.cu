@@ -362,6 +362,27 @@ __global__ void msm_combine_kernel(const G1Xyzz *window_sums, MsmCfg cfg, G1Xyzz
     }
 }
 
+// Σ of `count` projective (X:Y:Z) points given as 36-word records; one thread (count is a handful of ranks).
+__global__ void g1_sum_kernel(const uint32_t *pts, uint32_t count, uint32_t *result) {
+    G1Xyzz total = G1Xyzz::identity();
+    for (uint32_t i = 0; i < count; i++) {
+        Fp X, Y, Z;
+        for (int k = 0; k < 12; k++) { X.l[k] = pts[36 * i + k]; Y.l[k] = pts[36 * i + 12 + k]; Z.l[k] = pts[36 * i + 24 + k]; }
+        if (Z.is_zero()) continue;
+        // homogeneous (X:Y:Z) → XYZZ with ZZ = Z², ZZZ = Z³:  x = X/Z = X·Z/ZZ, y = Y/Z = Y·Z²/ZZZ
+        G1Xyzz p;
+        p.zz = Z.sqr();
+        p.zzz = p.zz * Z;
+        p.x = X * Z;
+        p.y = Y * p.zz;
+        total = g1_add(total, p);
+    }
+    G1Affine a;
+    Fp z = Fp::one();
+    if (!g1_to_affine(total, a)) { a.x = Fp::zero(); a.y = Fp::one(); z = Fp::zero(); }
+    for (int i = 0; i < 12; i++) { result[i] = a.x.l[i]; result[12 + i] = a.y.l[i]; result[24 + i] = z.l[i]; }
+}
+
 // ------------------------------------------------------------------------------ synthetic bases
 // bases[i] = (a + i·d)·G; each thread walks `per` consecutive points by repeated addition of d·G.
 __global__ void __launch_bounds__(128) synthetic_bases_kernel(G1Affine *out, uint64_t n, uint64_t a, uint64_t d, uint32_t per) {
@@ -621,6 +642,26 @@ extern "C" int pb200_msm_g1(pb200_ctx *ctx, const pb200_srs *srs, size_t offset,
     cudaFreeAsync(dev, ctx->stream);
     if (e != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "scalar upload", cudaGetErrorString(e), __FILE__, __LINE__);
     return rc;
+}
+extern "C" int pb200_g1_sum(pb200_ctx *ctx, const uint64_t *points_xyz_mont_host, size_t count, uint64_t out_xyz_mont[18]) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, out_xyz_mont != nullptr && (points_xyz_mont_host != nullptr || count == 0) && count <= 4096);
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *dev = nullptr;
+    PB_CUDA(ctx, cudaMallocAsync(&dev, (count + 1) * 144, ctx->stream));
+    uint32_t *pts = (uint32_t *)dev, *res = pts + 36 * count;
+    cudaError_t e = cudaSuccess;
+    if (count) e = cudaMemcpyAsync(pts, points_xyz_mont_host, count * 144, cudaMemcpyHostToDevice, ctx->stream);
+    g1_sum_kernel<<<1, 1, 0, ctx->stream>>>(pts, (uint32_t)count, res);
+    ctx->launches++;
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->pinned, res, 144, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+    cudaFreeAsync(dev, ctx->stream);
+    if (e != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "g1_sum", cudaGetErrorString(e), __FILE__, __LINE__);
+    if (e2 != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "g1_sum sync", cudaGetErrorString(e2), __FILE__, __LINE__);
+    memcpy(out_xyz_mont, ctx->pinned, 144);
+    return 0;
 }
 extern "C" int pb200_synthetic_bases_dev(pb200_ctx *ctx, uint64_t *xy_mont_dev, size_t n, uint64_t a, uint64_t d) {
     if (!ctx) return PB200_ERR_ARG;

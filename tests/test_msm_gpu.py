@@ -148,3 +148,21 @@ def test_closed_form_and_linearity_large(ctx, oracle, log_n):
     finally:
         ctx.free(bases)
         ctx.free(sd)
+
+
+def test_g1_sum_combines_partial_results(ctx, oracle):
+    """Point-range sharding: Σ over shards of MSM(shard) == MSM(whole)."""
+    n, parts = 4096, 4
+    pts = oracle.synthetic_bases(n)
+    s = oracle.fr_to_mont(oracle.random_fr(0x5A4D, n))
+    srs = ctx.srs_upload(pts)
+    try:
+        step = n // parts
+        partial = [ctx.msm(srs, s[i * step:(i + 1) * step], offset=i * step) for i in range(parts)]
+        partial.append(ctx.msm(srs, np.zeros((8, 4), np.uint64)))        # an identity in the mix
+        total = ctx.g1_sum(np.stack(partial))
+        assert aff(oracle, total) == aff(oracle, ctx.msm(srs, s))
+        assert aff(oracle, total) == aff(oracle, oracle.msm_variable_base(pts, s, threads=8))
+        assert aff(oracle, ctx.g1_sum(np.zeros((0, 18), np.uint64))) is None
+    finally:
+        ctx.srs_free(srs)
