@@ -87,6 +87,22 @@ def closed_form_scalar(scalars_mont, a, d):
     return total * pow(FR_MONT_R, -1, R_MOD) % R_MOD
 
 
+# -------------------------------------------------------------------------------------- sharding
+def shard_params(rank, n):
+    """Point-range sharding: rank r owns global indices [r·n, (r+1)·n) of the synthetic SRS,
+    i.e. bases (a_r + i·d)·G with a_r = a + r·n·d, and its own scalar stream."""
+    return {"a": A0 + rank * n * D0, "d": D0, "scalar_seed": 0xB2000000 + (n.bit_length() - 1) + 1000 * rank}
+
+
+def gather_partials(dist, local_u64x18, world, device):
+    """All-gather the 144-byte partial results (as int64) — the only collective on the MSM path."""
+    import torch
+    mine = torch.from_numpy(np.ascontiguousarray(local_u64x18).view(np.int64).copy()).to(device)
+    bufs = [torch.zeros(18, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(bufs, mine)
+    return torch.stack(bufs).cpu().numpy().view(np.uint64)
+
+
 # ---------------------------------------------------------------------------------------- clocks
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -198,7 +214,8 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
     L = args.log_n
     n = 1 << L
-    a_rank = A0 + rank * n * D0  # rank r owns the global index range [r·n, (r+1)·n)
+    shard = shard_params(rank, n)
+    a_rank = shard["a"]
 
     # --- inputs (untimed): resident SRS shard, scalars in pinned host memory and in HBM
     bases = ctx.malloc(n * 96)
@@ -206,7 +223,7 @@ def run_ours(args, rank, world, local_rank):
     srs = ctx.srs_wrap_dev(bases, n)
     pinned = torch.empty((n, 4), dtype=torch.int64, pin_memory=True)
     s_host = pinned.numpy().view(np.uint64)
-    random_fr_limbs(0xB2000000 + L + 1000 * rank, n, out=s_host)
+    random_fr_limbs(shard["scalar_seed"], n, out=s_host)
     s_dev = ctx.malloc(n * 32)
     ctx.h2d(s_dev, s_host)
 
@@ -215,8 +232,6 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
         ctx.sync()
-
-    gather_buf = torch.zeros((world, 18), dtype=torch.int64, device="cuda") if dist is not None else None
 
     def step_device():
         out = ctx.msm_dev(srs, s_dev, n)
@@ -229,10 +244,9 @@ def run_ours(args, rank, world, local_rank):
     def combine(out):
         if dist is None:
             return out
-        mine = torch.from_numpy(out.view(np.int64)).cuda()
-        dist.all_gather_into_tensor(gather_buf, mine)  # 144 B per rank over NVLink
+        parts = gather_partials(dist, out, world, torch.device("cuda", local_rank))  # 144 B per rank over NVLink
         if rank == 0:
-            return ctx.g1_sum(gather_buf.cpu().numpy().view(np.uint64))
+            return ctx.g1_sum(parts)
         return out
 
     # --- correctness of the full-size result (untimed): closed form over the global range
@@ -304,14 +318,18 @@ def run_ours(args, rank, world, local_rank):
             "bound": "imad", "kernel": "msm_accumulate_kernel",
             "achieved": alg_imad / (acc * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32 lane-op/s",
             "frac": alg_imad / (acc * 1e-3) / imad_peak, "traffic": None,
-            "peak_source": "pb200_imad_peak microbenchmark, this run (no integer peak in MEASURED_PEAKS.json)",
-            "model": "N*ceil(256/(log2N-4))*10 Fp mul * 300 IMAD.WIDE (SURVEY.md §8d; 600 lo/hi lane-ops = 300 wide)",
+            "peak_source": "pb200_imad_peak: IMAD.WIDE.U32.X carry-chain microbenchmark, this run (MEASURED_PEAKS.json has no "
+                           "integer peak); see profiles/imad_explore_r01.txt",
+            "model": "N*ceil(256/(log2N-4))*10 Fp mul * 300 IMAD.WIDE (SURVEY.md §8d: 600 lo+hi lane-ops at 64/clk/SM "
+                     "== 300 IMAD.WIDE at the measured 32/clk/SM)",
             "kernel_ms": acc, "share_of_step": acc / dev_ms,
             "whole_msm_frac": alg_imad / (dev_ms * 1e-3) / imad_peak,
             "phases_ms": {"sort": sum(sort_ms) / len(sort_ms), "accumulate": acc,
                           "partials": sum(part_ms) / len(part_ms), "reduce+combine": sum(red_ms) / len(red_ms)},
         }
         extra["ntt"] = bench_ntt(ctx, stream, args, imad_peak)
+        if not args.skip_prover_mix:
+            extra["prover_hot_path"] = bench_prover_mix(ctx, stream, args)
         cores = os.cpu_count() or 1
         sample_log = min(L, args.cpu_sample_log)
         pps, secs = cpu_msm_sample(sample_log, cores, 0xB2000000 + L)
@@ -427,6 +445,56 @@ def bench_ntt(ctx, stream, args, imad_peak):
     }
 
 
+def bench_prover_mix(ctx, stream, args):
+    """The MSM / NTT calls of ONE dusk-plonk 0.8 prove at n = 2^20 gates: 11 MSM(2^20),
+    10 NTT(2^20), 7 NTT(2^22) — device-resident, back to back.  Not a prover (rounds, transcript and the
+    quotient loop are SURVEY §8f "next"); it is the hot-path share a prover built on this backend pays."""
+    import torch
+    L = 20
+    n = 1 << L
+    bases = ctx.malloc(n * 96)
+    ctx.synthetic_bases_dev(bases, n, A0, D0)
+    srs = ctx.srs_wrap_dev(bases, n)
+    s = random_fr_limbs(0xB2000000 + L, n)
+    sd = ctx.malloc(n * 32)
+    ctx.h2d(sd, s)
+    poly = ctx.malloc(32 << 22)
+    ctx.h2d(poly, random_fr_limbs(0xF1F00016, 1 << 22))
+
+    def one_prove():
+        for i in range(11):
+            ctx.msm_dev(srs, sd, n)
+        for i in range(10):
+            ctx.ntt_dev(poly, 20, i & 1, 0)
+        for i in range(7):
+            ctx.ntt_dev(poly, 22, 1 if i == 6 else 0, 1)
+
+    for _ in range(2):
+        one_prove()
+    ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record(stream)
+    for _ in range(reps):
+        one_prove()
+    e1.record(stream)
+    ctx.sync()
+    ms = e0.elapsed_time(e1) / reps
+    # split
+    e0.record(stream)
+    for i in range(11):
+        ctx.msm_dev(srs, sd, n)
+    e1.record(stream)
+    ctx.sync()
+    msm_ms = e0.elapsed_time(e1)
+    ctx.srs_free(srs)
+    for b in (bases, sd, poly):
+        ctx.free(b)
+    return {"what": "11 MSM(2^20) + 10 NTT(2^20) + 7 coset NTT(2^22), device-resident (SURVEY.md §3.3 call mix of one prove)",
+            "ms": ms, "msm_ms": msm_ms, "ntt_ms": ms - msm_ms,
+            "note": "hot-path share only; the prover rounds themselves are out of this round's scope"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -436,6 +504,7 @@ def main():
     ap.add_argument("--log-n", type=int, default=26, help="log2 of MSM points per GPU")
     ap.add_argument("--ntt-log-n", type=int, default=24)
     ap.add_argument("--cpu-sample-log", type=int, default=20, help="log2 of the CPU baseline's bounded sample")
+    ap.add_argument("--skip-prover-mix", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -105,8 +105,9 @@ PB200_API int pb200_profile_enable(pb200_ctx *ctx, int on);
 PB200_API int pb200_profile_ms(pb200_ctx *ctx, const char *name, float *ms);
 /* Number of kernels this library has launched on the context since init (bench.py's gpu_launches). */
 PB200_API uint64_t pb200_launch_count(const pb200_ctx *ctx);
-/* Integer-pipe microbenchmark: sustained IMAD.WIDE.U32 (32×32+64) lane-operations per second over
- * the whole chip — the denominator of the MSM / NTT integer rooflines. */
+/* Integer-pipe microbenchmark: sustained IMAD.WIDE.U32.X (32×32+64 with carry) lane-operations per second
+ * over the whole chip — the denominator of the MSM / NTT integer rooflines.  The second output
+ * is that rate expressed as an SM clock assuming 32 lane-ops/clk/SM (the measured issue rate). */
 PB200_API int pb200_imad_peak(pb200_ctx *ctx, double *wide_lane_ops_per_s, double *sm_clock_mhz_est);
 
 #ifdef __cplusplus

@@ -99,30 +99,33 @@ extern "C" int pb200_profile_ms(pb200_ctx *ctx, const char *name, float *ms) {
 extern "C" uint64_t pb200_launch_count(const pb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 // ---------------------------------------------------------------------------------------------------
-// Integer-pipe microbenchmark.  Each thread runs 8 independent chains of mul.wide.u32 + add.u64
-// (→ IMAD.WIDE.U32 R, a, b, R) — the instruction both hot kernels are made of — long enough to
-// reach steady state.  Reported: lane-operations per second over the chip, and the SM clock implied
-// by clock64().
+// Integer-pipe microbenchmark.  Each thread runs carry chains of mul.wide.u32 + add.cc.u64/addc.cc.u64
+// (→ IMAD.WIDE.U32.X, the instruction both hot kernels are made of) over 8 accumulators whose low words
+// feed the next multiplicand, so ptxas cannot hoist or strength-reduce anything (an earlier version with a
+// loop-invariant product was folded away and reported a meaningless figure).  32 warps per SM.
+// Measured on B200: 32 lane-ops/clk/SM — IMAD.WIDE is half-rate, i.e. 64 lo+hi "32-bit IMAD" ops/clk/SM,
+// the planning figure of SURVEY.md §8d.  scripts/imad_explore.cu sweeps warps/SM and chain counts.
 namespace {
-__global__ void __launch_bounds__(256) imad_wide_kernel(uint64_t *sink, uint32_t iters, uint32_t a0, long long *cycles) {
+__global__ void __launch_bounds__(256) imad_wide_kernel(uint64_t *sink, uint32_t iters, uint32_t b0) {
     uint64_t acc[8];
-    uint32_t a = a0 + threadIdx.x, b = a0 * 3 + blockIdx.x;
+    const uint32_t b = b0 | 1u;
 #pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = (uint64_t)k * 0x9E3779B97F4A7C15ull + threadIdx.x;
-    long long t0 = clock64();
+    for (int k = 0; k < 8; k++) acc[k] = (uint64_t)(threadIdx.x + 1) * 0x9E3779B97F4A7C15ull + k * 77 + blockIdx.x;
     for (uint32_t i = 0; i < iters; i++) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
+        for (int r = 0; r < 16; r++) {
+            uint64_t p[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
+            for (int k = 0; k < 8; k++) p[k] = cc::mul_wide((uint32_t)acc[k], b);
+            acc[0] = cc::add_cc64(acc[0], p[0]);
+#pragma unroll
+            for (int k = 1; k < 8; k++) acc[k] = cc::addc_cc64(acc[k], p[k]);
         }
     }
-    long long t1 = clock64();
     uint64_t s = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) s ^= acc[k];
     sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
-    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
 }  // namespace
 
@@ -130,39 +133,30 @@ extern "C" int pb200_imad_peak(pb200_ctx *ctx, double *wide_lane_ops_per_s, doub
     if (!ctx) return PB200_ERR_ARG;
     PB_ARG(ctx, wide_lane_ops_per_s != nullptr);
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int blocks = ctx->sm_count * 8, threads = 256;
-    const uint32_t iters = 4096;
+    const int blocks = ctx->sm_count * 4, threads = 256;
+    const uint32_t iters = 2048;
     uint64_t *sink = nullptr;
-    long long *cyc = nullptr;
     PB_CUDA(ctx, cudaMalloc(&sink, (size_t)blocks * threads * 8));
-    PB_CUDA(ctx, cudaMalloc(&cyc, 8));
     cudaEvent_t e0, e1;
     PB_CUDA(ctx, cudaEventCreate(&e0));
     PB_CUDA(ctx, cudaEventCreate(&e1));
     float best = 1e30f;
-    long long cycles = 0;
     for (int rep = 0; rep < 5; rep++) {
         PB_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
-        imad_wide_kernel<<<blocks, threads, 0, ctx->stream>>>(sink, iters, 12345u + rep, cyc);
+        imad_wide_kernel<<<blocks, threads, 0, ctx->stream>>>(sink, iters, 12345u + rep);
         PB_LAUNCHED(ctx);
         PB_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         float ms = 0;
         PB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
-        if (rep > 0 && ms < best) {
-            best = ms;
-            PB_CUDA(ctx, cudaMemcpy(&cycles, cyc, 8, cudaMemcpyDeviceToHost));
-        }
+        if (rep > 0 && ms < best) best = ms;
     }
-    const double ops = (double)blocks * threads * (double)iters * 64.0;
+    const double ops = (double)blocks * threads * (double)iters * 16.0 * 8.0;
     *wide_lane_ops_per_s = ops / (best * 1e-3);
-    // block 0 executed iters·64 IMAD.WIDE per thread in `cycles` cycles while sharing its SM with 7 more
-    // CTAs; the kernel-wide clock estimate is total per-SM work / (rate implied by cycles) — simpler
-    // and robust: cycles of one CTA / wall time of the kernel is a lower bound on the clock.
-    if (sm_clock_mhz_est) *sm_clock_mhz_est = (double)cycles / (best * 1e-3) / 1e6;
+    // lane-ops per SM per second ÷ 32 lanes/clk (the measured issue rate) = the SM clock the run sustained
+    if (sm_clock_mhz_est) *sm_clock_mhz_est = *wide_lane_ops_per_s / ctx->sm_count / 32.0 / 1e6;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(sink);
-    cudaFree(cyc);
     return 0;
 }
