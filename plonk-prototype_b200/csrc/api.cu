@@ -35,6 +35,13 @@ extern "C" int pb200_init(pb200_ctx **out, int device_id) {
     *out = ctx;
     PB_CUDA(ctx, cudaSetDevice(device_id));
     PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {   // keep freed stream-ordered allocations in the pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     ctx->pinned_bytes = 1 << 16;
     PB_CUDA(ctx, cudaMallocHost(&ctx->pinned, ctx->pinned_bytes));
     PB_TRY(ntt_module_init(ctx));
@@ -47,6 +54,7 @@ extern "C" void pb200_destroy(pb200_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     ntt_free_plans(ctx);
     if (ctx->msm_ws) cudaFree(ctx->msm_ws);
+    if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

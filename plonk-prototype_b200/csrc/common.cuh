@@ -27,6 +27,8 @@ struct pb200_ctx {
     // MSM workspace (grown on demand, reused across calls)
     void *msm_ws = nullptr;
     size_t msm_ws_bytes = 0;
+    void *stage = nullptr;   // device staging for the host-buffer entry points (scalars / NTT vector)
+    size_t stage_bytes = 0;
     void *pinned = nullptr;  // small pinned staging block for results
     size_t pinned_bytes = 0;
 };

@@ -634,14 +634,9 @@ extern "C" int pb200_msm_g1(pb200_ctx *ctx, const pb200_srs *srs, size_t offset,
     if (n == 0) return msm_run(ctx, srs, offset, nullptr, 0, out_xyz_mont);
     PB_ARG(ctx, scalars_mont_host != nullptr);
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
-    void *dev = nullptr;
-    PB_CUDA(ctx, cudaMallocAsync(&dev, n * 32, ctx->stream));
-    cudaError_t e = cudaMemcpyAsync(dev, scalars_mont_host, n * 32, cudaMemcpyHostToDevice, ctx->stream);
-    int rc = 0;
-    if (e == cudaSuccess) rc = msm_run(ctx, srs, offset, (const uint64_t *)dev, n, out_xyz_mont);
-    cudaFreeAsync(dev, ctx->stream);
-    if (e != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "scalar upload", cudaGetErrorString(e), __FILE__, __LINE__);
-    return rc;
+    PB_TRY(pb_ensure(ctx, &ctx->stage, &ctx->stage_bytes, n * 32));
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->stage, scalars_mont_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    return msm_run(ctx, srs, offset, (const uint64_t *)ctx->stage, n, out_xyz_mont);
 }
 extern "C" int pb200_g1_sum(pb200_ctx *ctx, const uint64_t *points_xyz_mont_host, size_t count, uint64_t out_xyz_mont[18]) {
     if (!ctx) return PB200_ERR_ARG;

@@ -421,16 +421,10 @@ extern "C" int pb200_ntt(pb200_ctx *ctx, uint64_t *data_host, uint32_t log_n, in
     PB_ARG(ctx, log_n < kTwoAdicity);
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)32 << log_n;
-    void *dev = nullptr;
-    PB_CUDA(ctx, cudaMallocAsync(&dev, bytes, ctx->stream));
-    int rc = 0;
-    cudaError_t e = cudaMemcpyAsync(dev, data_host, bytes, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) rc = ntt_run(ctx, (Fr *)dev, log_n, inverse ? 1 : 0, coset ? 1 : 0);
-    if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(data_host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
-    cudaFreeAsync(dev, ctx->stream);
-    if (rc) return rc;
-    if (e != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "pb200_ntt copy", cudaGetErrorString(e), __FILE__, __LINE__);
-    if (e2 != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "pb200_ntt sync", cudaGetErrorString(e2), __FILE__, __LINE__);
+    PB_TRY(pb_ensure(ctx, &ctx->stage, &ctx->stage_bytes, bytes));
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->stage, data_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PB_TRY(ntt_run(ctx, (Fr *)ctx->stage, log_n, inverse ? 1 : 0, coset ? 1 : 0));
+    PB_CUDA(ctx, cudaMemcpyAsync(data_host, ctx->stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }

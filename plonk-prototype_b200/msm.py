@@ -28,6 +28,24 @@ def msm_variable_base(points, scalars, ctx=None):
         ctx.srs_free(srs)
 
 
+_P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+_RP_INV = pow(1 << 384, -1, _P)
+
+
+def g1_to_bytes(xyz):
+    """`G1Affine::from(G1Projective).to_bytes()` of dusk-bls12_381 (zcash format, SURVEY.md App. A.4) for the
+    normalised X‖Y‖Z the library returns: 48 bytes big-endian x; bit 7 = compressed, bit 6 = identity,
+    bit 5 = y is the lexicographically larger root.  One point, host-side, cold."""
+    v = [int(t) for t in np.asarray(xyz, dtype=np.uint64).reshape(18)]
+    if not any(v[12:]):
+        return bytes([0xC0]) + bytes(47)
+    x = sum(l << (64 * i) for i, l in enumerate(v[:6])) * _RP_INV % _P
+    y = sum(l << (64 * i) for i, l in enumerate(v[6:12])) * _RP_INV % _P
+    b = bytearray(x.to_bytes(48, "big"))
+    b[0] |= 0x80 | (0x20 if y > (_P - 1) // 2 else 0)
+    return bytes(b)
+
+
 class CommitKey:
     """`CommitKey { powers_of_g }` with the powers resident in HBM; `commit` = one MSM over the prefix."""
 
@@ -45,6 +63,10 @@ class CommitKey:
         if coeffs.shape[0] > self.n:
             raise ValueError("PolynomialDegreeTooLarge")  # dusk-plonk `check_degree_is_within_bounds`
         return self.ctx.msm(self._srs, coeffs)
+
+    def commit_bytes(self, coeffs):
+        """`Commitment::to_bytes()`: the 48-byte compressed commitment — the first byte-comparable artefact."""
+        return g1_to_bytes(self.commit(coeffs))
 
     def close(self):
         if self._srs is not None:

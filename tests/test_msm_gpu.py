@@ -25,6 +25,7 @@ def test_golden_vectors(ctx, oracle):
         got = aff(oracle, out)
         assert got == expected_affine(case), case["name"]
         assert model.g1_compress(got).hex() == case["compressed"]
+        assert pb.g1_to_bytes(out).hex() == case["compressed"]            # Commitment::to_bytes, byte-identical
         # result convention: Z = R for finite points, (0, R, 0) for the identity
         r1 = oracle.fp_consts()["r1"]
         if got is None:
