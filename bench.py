@@ -455,6 +455,7 @@ def bench_prover_mix(ctx, stream, args):
     bases = ctx.malloc(n * 96)
     ctx.synthetic_bases_dev(bases, n, A0, D0)
     srs = ctx.srs_wrap_dev(bases, n)
+    ctx.srs_precompute(srs)  # CommitKey set-up cost (once per circuit), not part of a prove
     s = random_fr_limbs(0xB2000000 + L, n)
     sd = ctx.malloc(n * 32)
     ctx.h2d(sd, s)

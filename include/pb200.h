@@ -13,9 +13,10 @@
  *     memory image of `Scalar.0` / `BlsScalar.0`.
  *   - Points: packed affine x[6] ‖ y[6] u64 limbs, Montgomery form (a·2^384 mod p), 96 bytes.  The
  *     identity is not encodable; callers drop identity bases (an SRS never holds one).
- *   - MSM result: projective X ‖ Y ‖ Z (18 × u64, Montgomery) normalised so Z = R (Montgomery 1) for
- *     a finite point and (0, R, 0) for the identity — i.e. the unique affine value embedded in
- *     `G1Projective`, which is what `G1Affine::from` / `to_bytes` would produce from any equal point.
+ *   - MSM result: homogeneous projective X ‖ Y ‖ Z (18 × u64, Montgomery) — the fields of `G1Projective`.
+ *     As with upstream's msm_variable_base the representative is NOT normalised (Z is an arbitrary non-zero
+ *     value for a finite point; the identity is (0, R, 0)); `G1Affine::from` / `to_bytes` on the caller's side
+ *     yield the canonical bytes, and only those are compared for parity.
  *   - All functions return 0 on success, non-zero on failure (pb200_last_error has the text).  No
  *     exception, abort or CPU fallback ever crosses this boundary; a missing GPU is an error.
  *   - A context is bound to one CUDA device and one stream and is not thread-safe.
@@ -79,6 +80,10 @@ PB200_API int pb200_ntt_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, 
 PB200_API int pb200_srs_upload(pb200_ctx *ctx, const uint64_t *xy_mont_host, size_t n_points, pb200_srs **out);
 /* Wrap bases that are already on the device (n_points × 96 B, not copied, not freed by srs_free). */
 PB200_API int pb200_srs_wrap_dev(pb200_ctx *ctx, const uint64_t *xy_mont_dev, size_t n_points, pb200_srs **out);
+/* Optional, once per SRS of at most 2^22 points: store the pre-doubled copies 2^(c·w)·P_i of every base so that
+ * all Pippenger windows share one bucket set — no per-window reduction and no Horner pass, which is what bounds
+ * prover-size (2^16…2^22) MSMs.  Costs W ≈ 12-13 times the SRS memory; results are unchanged. */
+PB200_API int pb200_srs_precompute(pb200_ctx *ctx, pb200_srs *srs);
 PB200_API void pb200_srs_free(pb200_ctx *ctx, pb200_srs *srs);
 PB200_API size_t pb200_srs_len(const pb200_srs *srs);
 /* msm_variable_base(&points[offset .. offset + n], scalars): Σ scalars[i]·points[offset + i].
@@ -90,7 +95,7 @@ PB200_API int pb200_msm_g1_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t offs
                      uint64_t out_xyz_mont[18]);
 /* Sum of `count` projective points (each X ‖ Y ‖ Z, 18 × u64 Montgomery, HOST memory) — the combine step after
  * a point-range-sharded MSM: every rank's partial result is gathered and added here.
- * Output normalised like pb200_msm_g1's. */
+ * Output as for pb200_msm_g1. */
 PB200_API int pb200_g1_sum(pb200_ctx *ctx, const uint64_t *points_xyz_mont_host, size_t count, uint64_t out_xyz_mont[18]);
 /* Pippenger window width used for n points (exposed for the benches' work model). */
 PB200_API uint32_t pb200_msm_window_bits(size_t n);

@@ -16,7 +16,7 @@ EXPORTS = [
     "pb200_init", "pb200_destroy", "pb200_last_error", "pb200_stream", "pb200_sync",
     "pb200_malloc", "pb200_free", "pb200_h2d", "pb200_d2h",
     "pb200_domain_log_size", "pb200_ntt", "pb200_ntt_dev",
-    "pb200_srs_upload", "pb200_srs_wrap_dev", "pb200_srs_free", "pb200_srs_len",
+    "pb200_srs_upload", "pb200_srs_wrap_dev", "pb200_srs_precompute", "pb200_srs_free", "pb200_srs_len",
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_g1_sum", "pb200_msm_window_bits",
     "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_launch_count",
     "pb200_imad_peak",
@@ -52,6 +52,7 @@ def lib():
         L.pb200_ntt_dev.argtypes = [vp, u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
         L.pb200_srs_upload.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.POINTER(vp)]
         L.pb200_srs_wrap_dev.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.POINTER(vp)]
+        L.pb200_srs_precompute.argtypes = [vp, vp]
         L.pb200_srs_free.argtypes = [vp, vp]
         L.pb200_srs_free.restype = None
         L.pb200_srs_len.argtypes = [vp]
@@ -149,6 +150,9 @@ class Context:
         h = ctypes.c_void_p()
         self._check(lib().pb200_srs_wrap_dev(self._h, ctypes.c_void_p(dev), n, ctypes.byref(h)))
         return h
+
+    def srs_precompute(self, srs):
+        self._check(lib().pb200_srs_precompute(self._h, srs))
 
     def srs_free(self, srs):
         lib().pb200_srs_free(self._h, srs)

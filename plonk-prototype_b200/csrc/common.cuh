@@ -37,6 +37,9 @@ struct pb200_srs {
     const uint64_t *dev = nullptr;
     size_t n = 0;
     bool owned = false;
+    // optional pre-doubled copies: pre[w·n + i] = 2^(c_pre·w)·P_i (affine), w < W_pre   (pb200_srs_precompute)
+    void *pre = nullptr;
+    uint32_t c_pre = 0, W_pre = 0;
 };
 
 inline int pb_fail(pb200_ctx *ctx, int code, const char *what, const char *detail, const char *file, int line) {

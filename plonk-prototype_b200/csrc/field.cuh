@@ -14,6 +14,13 @@
 #include "carry.cuh"
 
 template <class P>
+struct Field;
+#if defined(PB_FIELD_NOINLINE_MUL) && defined(__CUDACC__)
+template <class P>
+__device__ __noinline__ Field<P> field_mul_noinline(Field<P> a, Field<P> b);  // operands travel in registers
+#endif
+
+template <class P>
 struct Field {
     static constexpr int N = P::N;
     uint32_t l[N];
@@ -136,7 +143,7 @@ struct Field {
         S[H - 1] = cc::pack64(cc::lo32(S[H - 1]), cc::addc(cc::hi32(S[H - 1]), 0));
         redc_step(D, S);
     }
-    PB_HD friend Field operator*(const Field &a, const Field &b) {
+    PB_HD static Field mul_inline(const Field &a, const Field &b) {
         uint64_t A[H], B[H];
 #pragma unroll
         for (int k = 0; k < H; k++) {
@@ -161,6 +168,16 @@ struct Field {
         }
         r.l[N - 1] = cc::addc(cc::hi32(A[H - 1]), 0);
         return reduce_once(r);
+    }
+    // operator*: fully inlined in the throughput kernels; translation units that define
+    // PB_FIELD_NOINLINE_MUL (the latency-bound tail kernels) call one shared copy instead, which shrinks their
+    // code ~10× (cold instruction fetch dominated those single-warp kernels) and their register count.
+    PB_HD friend Field operator*(const Field &a, const Field &b) {
+#if defined(PB_FIELD_NOINLINE_MUL) && defined(__CUDA_ARCH__)
+        return field_mul_noinline(a, b);
+#else
+        return mul_inline(a, b);
+#endif
     }
     PB_HD Field sqr() const { return *this * *this; }
 
@@ -194,6 +211,13 @@ struct Field {
         return pow(e, N);
     }
 };
+
+#if defined(PB_FIELD_NOINLINE_MUL) && defined(__CUDACC__)
+template <class P>
+__device__ __noinline__ Field<P> field_mul_noinline(Field<P> a, Field<P> b) {
+    return Field<P>::mul_inline(a, b);
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------------
 // BLS12-381 scalar field Fr.  r ≡ 1 (mod 2^32) ⇒ −r⁻¹ mod 2^32 = 0xffffffff.

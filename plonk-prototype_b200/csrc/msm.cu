@@ -17,65 +17,9 @@
 #include <algorithm>
 #include <cstring>
 
-#include "common.cuh"
-#include "g1.cuh"
+#include "msm_common.cuh"
 
 namespace {
-
-constexpr uint32_t kInvalid = 0xffffffffu;
-constexpr uint32_t kScanItems = 4, kScanThreads = 1024, kScanTile = kScanItems * kScanThreads;
-
-struct MsmCfg {
-    uint32_t n;       // points in this piece (< 2^27)
-    uint32_t c;       // window bits
-    uint32_t W;       // windows = ceil(256 / c)
-    uint32_t nb_log;  // log2 buckets per window = c − 1
-    uint32_t L1, L2;  // segment length at level 1 / higher levels
-    uint32_t K_log;   // log2 buckets per reduction chunk
-};
-
-// ------------------------------------------------------------------------------------------ loads
-__device__ __forceinline__ Fr load_fr(const uint64_t *scalars, size_t i) {
-    const uint4 *q = reinterpret_cast<const uint4 *>(scalars + 4 * i);
-    uint4 a = q[0], b = q[1];
-    Fr r;
-    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
-    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
-    return r;
-}
-__device__ __forceinline__ void load_fp2(const uint4 *q, Fp &a, Fp &b) {
-    uint4 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3], v4 = q[4], v5 = q[5];
-    a.l[0] = v0.x; a.l[1] = v0.y; a.l[2] = v0.z; a.l[3] = v0.w; a.l[4] = v1.x; a.l[5] = v1.y;
-    a.l[6] = v1.z; a.l[7] = v1.w; a.l[8] = v2.x; a.l[9] = v2.y; a.l[10] = v2.z; a.l[11] = v2.w;
-    b.l[0] = v3.x; b.l[1] = v3.y; b.l[2] = v3.z; b.l[3] = v3.w; b.l[4] = v4.x; b.l[5] = v4.y;
-    b.l[6] = v4.z; b.l[7] = v4.w; b.l[8] = v5.x; b.l[9] = v5.y; b.l[10] = v5.z; b.l[11] = v5.w;
-}
-__device__ __forceinline__ void store_fp2(uint4 *q, const Fp &a, const Fp &b) {
-    q[0] = make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]);
-    q[1] = make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]);
-    q[2] = make_uint4(a.l[8], a.l[9], a.l[10], a.l[11]);
-    q[3] = make_uint4(b.l[0], b.l[1], b.l[2], b.l[3]);
-    q[4] = make_uint4(b.l[4], b.l[5], b.l[6], b.l[7]);
-    q[5] = make_uint4(b.l[8], b.l[9], b.l[10], b.l[11]);
-}
-__device__ __forceinline__ G1Affine load_affine(const G1Affine *bases, uint32_t idx_sign) {
-    G1Affine p;
-    load_fp2(reinterpret_cast<const uint4 *>(bases + (idx_sign & 0x7fffffffu)), p.x, p.y);
-    if (idx_sign >> 31) p.y = p.y.neg();
-    return p;
-}
-__device__ __forceinline__ G1Xyzz load_xyzz(const G1Xyzz *p) {
-    G1Xyzz r;
-    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-    load_fp2(q, r.x, r.y);
-    load_fp2(q + 6, r.zz, r.zzz);
-    return r;
-}
-__device__ __forceinline__ void store_xyzz(G1Xyzz *p, const G1Xyzz &v) {
-    uint4 *q = reinterpret_cast<uint4 *>(p);
-    store_fp2(q, v.x, v.y);
-    store_fp2(q + 6, v.zz, v.zzz);
-}
 
 // --------------------------------------------------------------------------------- digit recoding
 // Signed-digit decomposition of a canonical 255-bit scalar into W digits of c bits:
@@ -104,7 +48,7 @@ __global__ void __launch_bounds__(256) msm_count_kernel(const uint64_t *scalars,
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cfg.n; i += (size_t)gridDim.x * blockDim.x) {
         Fr s = load_fr(scalars, i).from_mont();
         for_each_digit(s, cfg.c, cfg.W, [&](uint32_t w, uint32_t mag, uint32_t) {
-            atomicAdd(&count[(w << cfg.nb_log) + mag - 1], 1u);
+            atomicAdd(&count[(cfg.pre_stride ? 0u : (w << cfg.nb_log)) + mag - 1], 1u);
         });
     }
 }
@@ -112,9 +56,9 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint64_t *scalar
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cfg.n; i += (size_t)gridDim.x * blockDim.x) {
         Fr s = load_fr(scalars, i).from_mont();
         for_each_digit(s, cfg.c, cfg.W, [&](uint32_t w, uint32_t mag, uint32_t sign) {
-            const uint32_t gb = (w << cfg.nb_log) + mag - 1;
+            const uint32_t gb = (cfg.pre_stride ? 0u : (w << cfg.nb_log)) + mag - 1;
             const uint32_t pos = atomicAdd(&cursor[gb], 1u);
-            entries[pos] = make_uint2(gb, (uint32_t)i | (sign << 31));
+            entries[pos] = make_uint2(gb, (uint32_t)(w * cfg.pre_stride + i) | (sign << 31));
         });
     }
 }
@@ -187,39 +131,6 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
     }
 }
 
-// ------------------------------------------------------------------------------------ accumulate
-// Output rule shared by every level.  A run that lies strictly inside its segment is complete and
-// goes to its bucket.  A run that touches the left (right) segment boundary *and* continues in the
-// neighbouring segment is a partial: left-touching partials go to the head slot, right-touching
-// ones to the tail slot; a run touching both sides stores its sum in the head slot and the identity
-// in the tail slot, so all partials of one bucket stay contiguous in slot order (no holes inside).
-struct RunSink {
-    G1Xyzz *buckets;
-    uint32_t *out_gb;
-    G1Xyzz *out_pt;
-    uint32_t t;
-    uint32_t head_gb, tail_gb;
-    __device__ __forceinline__ void flush(uint32_t gb, const G1Xyzz &acc, bool tl, bool tr) {
-        if (!tl && !tr) {
-            store_xyzz(buckets + gb, acc);
-        } else if (tl) {
-            head_gb = gb;
-            store_xyzz(out_pt + 2 * (size_t)t, acc);
-            if (tr) {
-                tail_gb = gb;
-                store_xyzz(out_pt + 2 * (size_t)t + 1, G1Xyzz::identity());
-            }
-        } else {
-            tail_gb = gb;
-            store_xyzz(out_pt + 2 * (size_t)t + 1, acc);
-        }
-    }
-    __device__ __forceinline__ void finish() {
-        out_gb[2 * (size_t)t] = head_gb;
-        out_gb[2 * (size_t)t + 1] = tail_gb;
-    }
-};
-
 // Level 1: entries (bucket id, point index | sign) → buckets / partial slots, mixed additions.
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine *__restrict__ bases, const uint2 *__restrict__ entries,
                                                              const uint32_t *__restrict__ n_entries_ptr, uint32_t L,
@@ -260,153 +171,16 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine *__r
     sink.flush(cur, acc, tl, next == cur);
     sink.finish();
 }
-// Levels ≥ 2: partial slots (bucket id or kInvalid, XYZZ point) → buckets / next-level slots.
-__global__ void __launch_bounds__(128) msm_accumulate_slots_kernel(const uint32_t *__restrict__ in_gb, const G1Xyzz *__restrict__ in_pt,
-                                                                   const uint32_t *__restrict__ n_in_ptr, uint32_t L,
-                                                                   G1Xyzz *buckets, uint32_t *out_gb, G1Xyzz *out_pt,
-                                                                   uint32_t *n_out_ptr) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n_in = *n_in_ptr;
-    if (t == 0) *n_out_ptr = 2 * (uint32_t)(((uint64_t)n_in + L - 1) / L);
-    const uint64_t start64 = (uint64_t)t * L;
-    if (start64 >= n_in) return;
-    const uint32_t start = (uint32_t)start64, end = (uint32_t)min((uint64_t)n_in, start64 + L);
-    const uint32_t prev = start > 0 ? in_gb[start - 1] : kInvalid;
-    const uint32_t next = end < n_in ? in_gb[end] : kInvalid;
-    RunSink sink{buckets, out_gb, out_pt, t, kInvalid, kInvalid};
-
-    uint32_t cur = kInvalid;
-    bool have = false, tl = false;
-    G1Xyzz acc = G1Xyzz::identity();
-    for (uint32_t i = start; i < end; i++) {
-        const uint32_t gb = in_gb[i];
-        if (have && gb != cur) {  // a different bucket or a hole ends the run
-            sink.flush(cur, acc, tl, false);
-            have = false;
-        }
-        if (gb == kInvalid) continue;
-        if (!have) {
-            have = true;
-            cur = gb;
-            tl = (i == start && prev == gb);
-            acc = G1Xyzz::identity();
-        }
-        acc = g1_add(acc, load_xyzz(in_pt + i));
+// Window width with pre-doubled copies: one shared bucket set, so only W·n additions + one reduction of 2^(c−1) buckets.
+uint32_t choose_window_pre(size_t n) {
+    uint32_t best_c = 8;
+    double best = 1e300;
+    for (uint32_t c = 8; c <= 23; c++) {
+        const double W = (256 + c - 1) / c;
+        const double cost = W * (double)n + 3.0 * (double)(1u << (c - 1));
+        if (cost <= best) { best = cost; best_c = c; }
     }
-    if (have) sink.flush(cur, acc, tl, next == cur);
-    sink.finish();
-}
-
-// ---------------------------------------------------------------------------------------- reduce
-// One thread per chunk of K consecutive buckets of one window:
-//   Σ_{j<K} (qK + j + 1)·B_{qK+j} = Σ_j (j+1)·B_j  (running sum)  +  (qK)·Σ_j B_j  (small scalar mul)
-__global__ void __launch_bounds__(128) msm_reduce_chunks_kernel(const G1Xyzz *__restrict__ buckets, const uint32_t *__restrict__ count,
-                                                                MsmCfg cfg, G1Xyzz *chunk_sums) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t chunks_log = cfg.nb_log - cfg.K_log;
-    if (t >= (cfg.W << chunks_log)) return;
-    const uint32_t w = t >> chunks_log, q = t & ((1u << chunks_log) - 1), K = 1u << cfg.K_log;
-    const uint32_t base = (w << cfg.nb_log) + (q << cfg.K_log);
-    G1Xyzz run = G1Xyzz::identity(), acc = G1Xyzz::identity();
-    for (int j = (int)K - 1; j >= 0; j--) {
-        if (count[base + j]) run = g1_add(run, load_xyzz(buckets + base + j));
-        acc = g1_add(acc, run);
-    }
-    if (q) acc = g1_add(acc, g1_mul_small(run, (uint64_t)q << cfg.K_log));
-    store_xyzz(chunk_sums + t, acc);
-}
-// One CTA per window: tree sum of its chunk sums.
-__global__ void __launch_bounds__(128) msm_window_sum_kernel(const G1Xyzz *__restrict__ chunk_sums, uint32_t chunks_per_window,
-                                                             G1Xyzz *window_sums) {
-    __shared__ uint4 sm[128 * 12];
-    const uint32_t w = blockIdx.x, tid = threadIdx.x;
-    G1Xyzz acc = G1Xyzz::identity();
-    for (uint32_t i = tid; i < chunks_per_window; i += blockDim.x)
-        acc = g1_add(acc, load_xyzz(chunk_sums + (size_t)w * chunks_per_window + i));
-    G1Xyzz *smp = reinterpret_cast<G1Xyzz *>(sm);
-    store_xyzz(smp + tid, acc);
-    __syncthreads();
-    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-        if (tid < s) {
-            acc = g1_add(load_xyzz(smp + tid), load_xyzz(smp + tid + s));
-            store_xyzz(smp + tid, acc);
-        }
-        __syncthreads();
-    }
-    if (tid == 0) store_xyzz(window_sums + w, acc);
-}
-// Horner over the windows, optional accumulation across pieces, normalisation to affine.
-// result: 36 words — x[12] ‖ y[12] ‖ z[12] with z = R (finite) or (0, R, 0) for the identity.
-__global__ void msm_combine_kernel(const G1Xyzz *window_sums, MsmCfg cfg, G1Xyzz *running_total, int first_piece,
-                                   int last_piece, uint32_t *result) {
-    G1Xyzz total = G1Xyzz::identity();
-    for (int w = (int)cfg.W - 1; w >= 0; w--) {
-        for (uint32_t k = 0; k < cfg.c; k++) total = g1_dbl(total);
-        total = g1_add(total, load_xyzz(window_sums + w));
-    }
-    if (!first_piece) total = g1_add(total, load_xyzz(running_total));
-    store_xyzz(running_total, total);
-    if (last_piece) {
-        G1Affine a;
-        Fp z = Fp::one();
-        if (!g1_to_affine(total, a)) {
-            a.x = Fp::zero();
-            a.y = Fp::one();
-            z = Fp::zero();
-        }
-        for (int i = 0; i < 12; i++) {
-            result[i] = a.x.l[i];
-            result[12 + i] = a.y.l[i];
-            result[24 + i] = z.l[i];
-        }
-    }
-}
-
-// Σ of `count` projective (X:Y:Z) points given as 36-word records; one thread (count is a handful of ranks).
-__global__ void g1_sum_kernel(const uint32_t *pts, uint32_t count, uint32_t *result) {
-    G1Xyzz total = G1Xyzz::identity();
-    for (uint32_t i = 0; i < count; i++) {
-        Fp X, Y, Z;
-        for (int k = 0; k < 12; k++) { X.l[k] = pts[36 * i + k]; Y.l[k] = pts[36 * i + 12 + k]; Z.l[k] = pts[36 * i + 24 + k]; }
-        if (Z.is_zero()) continue;
-        // homogeneous (X:Y:Z) → XYZZ with ZZ = Z², ZZZ = Z³:  x = X/Z = X·Z/ZZ, y = Y/Z = Y·Z²/ZZZ
-        G1Xyzz p;
-        p.zz = Z.sqr();
-        p.zzz = p.zz * Z;
-        p.x = X * Z;
-        p.y = Y * p.zz;
-        total = g1_add(total, p);
-    }
-    G1Affine a;
-    Fp z = Fp::one();
-    if (!g1_to_affine(total, a)) { a.x = Fp::zero(); a.y = Fp::one(); z = Fp::zero(); }
-    for (int i = 0; i < 12; i++) { result[i] = a.x.l[i]; result[12 + i] = a.y.l[i]; result[24 + i] = z.l[i]; }
-}
-
-// ------------------------------------------------------------------------------ synthetic bases
-// bases[i] = (a + i·d)·G; each thread walks `per` consecutive points by repeated addition of d·G.
-__global__ void __launch_bounds__(128) synthetic_bases_kernel(G1Affine *out, uint64_t n, uint64_t a, uint64_t d, uint32_t per) {
-    const uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    const uint64_t i0 = t * per;
-    if (i0 >= n) return;
-    // G1 generator, Montgomery form
-    G1Affine g;
-    {
-        const uint32_t gx[12] = {0xfd530c16u, 0x5cb38790u, 0x9976fff5u, 0x7817fc67u, 0x143ba1c1u, 0x154f95c7u,
-                                 0xf3d0e747u, 0xf0ae6acdu, 0x21dbf440u, 0xedce6eccu, 0x9e0bfb75u, 0x12017741u};
-        const uint32_t gy[12] = {0x0ce72271u, 0xbaac93d5u, 0x7918fd8eu, 0x8c22631au, 0x570725ceu, 0xdd595f13u,
-                                 0x50405194u, 0x51ac5829u, 0xad0059c0u, 0x0e1c8c3fu, 0x5008a26au, 0x0bbc3efcu};
-        for (int k = 0; k < 12; k++) { g.x.l[k] = gx[k]; g.y.l[k] = gy[k]; }
-    }
-    const G1Xyzz G = G1Xyzz::from_affine(g);
-    G1Xyzz cur = g1_mul_small(G, a + i0 * d);
-    const G1Xyzz step = g1_mul_small(G, d);
-    for (uint32_t k = 0; k < per && i0 + k < n; k++) {
-        G1Affine af;
-        g1_to_affine(cur, af);  // (a + i·d) is never ≡ 0 mod r for the sizes used
-        store_fp2(reinterpret_cast<uint4 *>(out + i0 + k), af.x, af.y);
-        cur = g1_add(cur, step);
-    }
+    return best_c;
 }
 
 // Window width minimising W·(n + 3·2^(c−1)): n·W mixed additions plus ≈ 3 addition-equivalents per bucket
@@ -435,23 +209,25 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // One piece (n < 2^27) of an MSM; bases / scalars on the device.
 static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scalars, uint32_t n, int first, int last,
-                     G1Xyzz *running_total, uint32_t *result_dev) {
+                     G1Xyzz *running_total, uint32_t *result_dev, uint32_t pre_c, uint32_t pre_stride) {
     MsmCfg cfg;
     cfg.n = n;
-    cfg.c = choose_window(n);
+    cfg.c = pre_stride ? pre_c : choose_window(n);
     cfg.W = (256 + cfg.c - 1) / cfg.c;
     cfg.nb_log = cfg.c - 1;
+    cfg.pre_stride = pre_stride;
     const uint64_t m0 = (uint64_t)n * cfg.W;  // upper bound on entries
     PB_ARG(ctx, m0 < (1ull << 32));
     cfg.L1 = std::min<uint32_t>(128, std::max<uint32_t>(8, floor_pow2(m0 / 262144 + 1)));
     cfg.L2 = 16;
-    const uint32_t TB = cfg.W << cfg.nb_log;  // total buckets
+    const uint32_t n_win = pre_stride ? 1u : cfg.W;   // bucket sets (windows to reduce / combine)
+    const uint32_t TB = n_win << cfg.nb_log;          // total buckets
     {   // chunk size for the bucket reduction: aim for ≥ 64 Ki chunk threads, 8 ≤ K ≤ 256
         uint32_t k_log = 3;
         while (k_log < 8 && (TB >> (k_log + 1)) >= 65536) k_log++;
         cfg.K_log = std::min(k_log, cfg.nb_log);
     }
-    const uint32_t n_chunks = TB >> cfg.K_log, chunks_per_window = n_chunks / cfg.W;
+    const uint32_t n_chunks = TB >> cfg.K_log, chunks_per_window = n_chunks / n_win;
 
     // level bounds
     std::vector<uint32_t> lvl_threads, lvl_slots;
@@ -474,7 +250,10 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     const size_t slotsA = lvl_slots[0], slotsB = lvl_slots.size() > 1 ? lvl_slots[1] : 2;
     const size_t o_gbA = carve(slotsA * 4), o_ptA = carve(slotsA * sizeof(G1Xyzz));
     const size_t o_gbB = carve(slotsB * 4), o_ptB = carve(slotsB * sizeof(G1Xyzz));
-    const size_t o_chunks = carve((size_t)n_chunks * sizeof(G1Xyzz)), o_wsum = carve((size_t)cfg.W * sizeof(G1Xyzz));
+    const size_t o_chunks = carve((size_t)n_chunks * sizeof(G1Xyzz)), o_wsum = carve((size_t)n_win * sizeof(G1Xyzz));
+    // two-stage window sum when a window has many chunk sums: ≤ 4 items per thread in the first stage
+    const uint32_t sum_parts = std::min<uint32_t>(256, (chunks_per_window + 511) / 512);
+    const size_t o_psum = carve((size_t)n_win * sum_parts * sizeof(G1Xyzz));
     PB_TRY(pb_ensure(ctx, &ctx->msm_ws, &ctx->msm_ws_bytes, off));
     char *ws = (char *)ctx->msm_ws;
     uint32_t *count = (uint32_t *)(ws + o_count), *cursor = (uint32_t *)(ws + o_cursor), *bsum = (uint32_t *)(ws + o_bsum);
@@ -483,7 +262,7 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     G1Xyzz *buckets = (G1Xyzz *)(ws + o_buckets);
     uint32_t *gbA = (uint32_t *)(ws + o_gbA), *gbB = (uint32_t *)(ws + o_gbB);
     G1Xyzz *ptA = (G1Xyzz *)(ws + o_ptA), *ptB = (G1Xyzz *)(ws + o_ptB);
-    G1Xyzz *chunks = (G1Xyzz *)(ws + o_chunks), *wsum = (G1Xyzz *)(ws + o_wsum);
+    G1Xyzz *chunks = (G1Xyzz *)(ws + o_chunks), *wsum = (G1Xyzz *)(ws + o_wsum), *psum = (G1Xyzz *)(ws + o_psum);
     cudaStream_t st = ctx->stream;
 
     PbTimer t_sort(ctx, "msm.sort");
@@ -510,26 +289,27 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
         uint32_t *in_gb = gbA, *out_gb = gbB;
         G1Xyzz *in_pt = ptA, *out_pt = ptB;
         for (size_t k = 1; k < lvl_threads.size(); k++) {
-            msm_accumulate_slots_kernel<<<(lvl_threads[k] + 127) / 128, 128, 0, st>>>(in_gb, in_pt, meta + k, cfg.L2, buckets, out_gb,
-                                                                                      out_pt, meta + k + 1);
-            PB_LAUNCHED(ctx);
+            PB_TRY(tail_accumulate_slots(ctx, lvl_threads[k], in_gb, in_pt, meta + k, cfg.L2, buckets, out_gb, out_pt, meta + k + 1));
             std::swap(in_gb, out_gb);
             std::swap(in_pt, out_pt);
         }
         // whatever is left (≤ 32 slots) is finished by one thread: no neighbours, so every run is complete
-        msm_accumulate_slots_kernel<<<1, 1, 0, st>>>(in_gb, in_pt, meta + lvl_threads.size(), 0x7fffffffu, buckets, out_gb, out_pt,
-                                                      meta + lvl_threads.size() + 1);
-        PB_LAUNCHED(ctx);
+        PB_TRY(tail_accumulate_slots(ctx, 1, in_gb, in_pt, meta + lvl_threads.size(), 0x7fffffffu, buckets, out_gb, out_pt,
+                                     meta + lvl_threads.size() + 1));
     }
     t_fix.stop();
 
     PbTimer t_red(ctx, "msm.reduce");
-    msm_reduce_chunks_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(buckets, count, cfg, chunks);
-    PB_LAUNCHED(ctx);
-    msm_window_sum_kernel<<<cfg.W, 128, 0, st>>>(chunks, chunks_per_window, wsum);
-    PB_LAUNCHED(ctx);
-    msm_combine_kernel<<<1, 1, 0, st>>>(wsum, cfg, running_total, first, last, result_dev);
-    PB_LAUNCHED(ctx);
+    MsmCfg rcfg = cfg;
+    rcfg.W = n_win;
+    PB_TRY(tail_reduce_chunks(ctx, n_chunks, buckets, count, rcfg, chunks));
+    if (sum_parts > 1) {
+        PB_TRY(tail_sum(ctx, n_win, sum_parts, chunks, chunks_per_window, psum));
+        PB_TRY(tail_sum(ctx, n_win, 1, psum, sum_parts, wsum));
+    } else {
+        PB_TRY(tail_sum(ctx, n_win, 1, chunks, chunks_per_window, wsum));
+    }
+    PB_TRY(tail_combine(ctx, wsum, rcfg, running_total, first, last, result_dev));
     t_red.stop();
     if (ctx->profile) {
         PB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -555,6 +335,9 @@ static int msm_run(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const ui
     PB_ARG(ctx, scalars_dev != nullptr);
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     const G1Affine *bases = reinterpret_cast<const G1Affine *>(srs->dev) + offset;
+    // pre-doubled copies pay off unless the call touches a small fraction of the SRS (the bucket count is sized for it)
+    const bool use_pre = srs->pre != nullptr && n * 16 >= srs->n && (uint64_t)srs->W_pre * srs->n < (1ull << 31);
+    if (use_pre) bases = reinterpret_cast<const G1Affine *>(srs->pre) + offset;
     void *small = nullptr;  // running total (XYZZ) + result (36 words)
     PB_CUDA(ctx, cudaMallocAsync(&small, sizeof(G1Xyzz) + 36 * 4, ctx->stream));
     G1Xyzz *running = (G1Xyzz *)small;
@@ -564,7 +347,8 @@ static int msm_run(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const ui
     int rc = 0;
     for (size_t done = 0; done < n && rc == 0; done += piece) {
         const uint32_t m = (uint32_t)std::min(piece, n - done);
-        rc = msm_piece(ctx, bases + done, scalars_dev + 4 * done, m, done == 0, done + m == n, running, result);
+        rc = msm_piece(ctx, bases + done, scalars_dev + 4 * done, m, done == 0, done + m == n, running, result,
+                       use_pre ? srs->c_pre : 0, use_pre ? (uint32_t)srs->n : 0);
     }
     t_total.stop();
     cudaError_t e = cudaSuccess;
@@ -610,8 +394,32 @@ extern "C" int pb200_srs_wrap_dev(pb200_ctx *ctx, const uint64_t *xy_mont_dev, s
     *out = s;
     return 0;
 }
+extern "C" int pb200_srs_precompute(pb200_ctx *ctx, pb200_srs *srs) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, srs != nullptr && srs->dev != nullptr);
+    PB_ARG(ctx, srs->n >= 1 && srs->n <= ((size_t)1 << 22));
+    if (srs->pre) return 0;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t c = choose_window_pre(srs->n), W = (256 + c - 1) / c;
+    void *pre = nullptr;
+    PB_CUDA(ctx, cudaMalloc(&pre, (size_t)W * srs->n * sizeof(G1Affine)));
+    int rc = tail_precompute(ctx, reinterpret_cast<const G1Affine *>(srs->dev), (uint32_t)srs->n, c, W, (G1Affine *)pre);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (rc != 0 || e != cudaSuccess) {
+        cudaFree(pre);
+        return rc ? rc : pb_fail(ctx, PB200_ERR_CUDA, "srs precompute", cudaGetErrorString(e), __FILE__, __LINE__);
+    }
+    srs->pre = pre;
+    srs->c_pre = c;
+    srs->W_pre = W;
+    return 0;
+}
 extern "C" void pb200_srs_free(pb200_ctx *ctx, pb200_srs *srs) {
     if (!srs) return;
+    if (srs->pre) {
+        if (ctx) cudaStreamSynchronize(ctx->stream);
+        cudaFree(srs->pre);
+    }
     if (srs->owned && srs->dev) {
         if (ctx) cudaStreamSynchronize(ctx->stream);
         cudaFree((void *)srs->dev);
@@ -647,9 +455,7 @@ extern "C" int pb200_g1_sum(pb200_ctx *ctx, const uint64_t *points_xyz_mont_host
     uint32_t *pts = (uint32_t *)dev, *res = pts + 36 * count;
     cudaError_t e = cudaSuccess;
     if (count) e = cudaMemcpyAsync(pts, points_xyz_mont_host, count * 144, cudaMemcpyHostToDevice, ctx->stream);
-    g1_sum_kernel<<<1, 1, 0, ctx->stream>>>(pts, (uint32_t)count, res);
-    ctx->launches++;
-    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess && tail_g1_sum(ctx, pts, (uint32_t)count, res) != 0) e = cudaErrorLaunchFailure;
     if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->pinned, res, 144, cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     cudaFreeAsync(dev, ctx->stream);
@@ -663,10 +469,7 @@ extern "C" int pb200_synthetic_bases_dev(pb200_ctx *ctx, uint64_t *xy_mont_dev, 
     PB_ARG(ctx, xy_mont_dev != nullptr || n == 0);
     if (n == 0) return 0;
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
-    const uint32_t per = 32;
-    const uint64_t threads = (n + per - 1) / per;
-    synthetic_bases_kernel<<<(uint32_t)((threads + 127) / 128), 128, 0, ctx->stream>>>((G1Affine *)xy_mont_dev, n, a, d, per);
-    PB_LAUNCHED(ctx);
+    PB_TRY(tail_synthetic_bases(ctx, (G1Affine *)xy_mont_dev, n, a, d));
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }

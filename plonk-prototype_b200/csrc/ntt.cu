@@ -29,13 +29,15 @@ struct NttPass {
     uint32_t ncol_log;   // type 0: log2(columns per row block)
     uint32_t nrows_log;  // type 1: log2(number of rows) = log n − S
     uint32_t n1_log;     // type 1: log2 of the first-pass length (row ↔ natural-index digit swap)
-    uint32_t load_mode;  // 0 none | 1 × lo[e]·hi[e] with e = natural input index        (coset_fft)
+    uint32_t load_mode;  // 0 none | 1 × lo[e]·hi[e], e = natural input index | 2 × full[e]           (coset_fft)
     uint32_t store_mode; // 0 none | 1 × constant | 2 × pow(col·k << mult_log) | 3 × pow(natural output index)
+                         // 4 × full[(k << ncol_log) + col] (inter-pass twiddle, one lookup) | 5 × full[natural output index]
     uint32_t mult_log;
     uint32_t l_B, s_B;   // split point of the two-level power tables
     const Fr *tw;        // ω_{2^S}^j, j < 2^(S−1)
     const Fr *l_lo, *l_hi, *s_lo, *s_hi;
     const Fr *s_const;
+    const Fr *l_full, *s_full;  // single-lookup tables (one multiply instead of two)
 };
 
 __device__ __forceinline__ Fr g_load(const Fr *p) {
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const Fr *__restrict__
         }
         Fr v = g_load(in + addr);
         if (p.load_mode == 1) v = v * pow2level(p.l_lo, p.l_hi, p.l_B, (uint32_t)addr);
+        else if (p.load_mode == 2) v = v * g_load(p.l_full + addr);
         sm_store(sm, PS, (x << logC) + c, v);
     }
     __syncthreads();
@@ -199,9 +202,11 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const Fr *__restrict__
         if (p.type == 0) {
             addr = in_base + ((uint64_t)k << p.ncol_log) + c;
             if (p.store_mode == 2) v = v * pow2level(p.s_lo, p.s_hi, p.s_B, ((col0 + c) * k) << p.mult_log);
+            else if (p.store_mode == 4) v = v * g_load(p.s_full + (((uint64_t)k << p.ncol_log) + col0 + c));
         } else {
             addr = (uint64_t)(rowrev0 + c) + ((uint64_t)k << p.nrows_log);
             if (p.store_mode == 3) v = v * pow2level(p.s_lo, p.s_hi, p.s_B, (uint32_t)addr);
+            else if (p.store_mode == 5) v = v * g_load(p.s_full + addr);
         }
         if (p.store_mode == 1) v = v * g_load(p.s_const);
         g_store(out + addr, v);
@@ -257,6 +262,21 @@ __global__ void fill_powers_kernel(Fr *out, uint32_t count, const Fr *base, uint
     g_store(out + j, p * b.pow_u64((uint64_t)j * stride));
 }
 
+// full[(k << ncol_log) + j] = lo/hi-composed base^((j·k) << mult_log), j < 2^ncol_log, k < 2^S
+__global__ void fill_boundary_kernel(Fr *out, uint32_t S, uint32_t ncol_log, uint32_t mult_log, const Fr *lo, const Fr *hi,
+                                     uint32_t B) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= (1ull << (S + ncol_log))) return;
+    const uint32_t j = (uint32_t)(i & ((1ull << ncol_log) - 1)), k = (uint32_t)(i >> ncol_log);
+    g_store(out + i, pow2level(lo, hi, B, (j * k) << mult_log));
+}
+// full[e] = lo[e & mask]·hi[e >> B], e < 2^L
+__global__ void fill_linear_kernel(Fr *out, uint32_t L, const Fr *lo, const Fr *hi, uint32_t B) {
+    const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (i >= (1ull << L)) return;
+    g_store(out + i, pow2level(lo, hi, B, (uint32_t)i));
+}
+
 }  // namespace
 
 struct NttPlan {
@@ -266,7 +286,13 @@ struct NttPlan {
     NttPass pass[3];
     Fr *consts = nullptr;
     std::vector<void *> allocs;
+    size_t table_bytes = 0;
 };
+
+static uint32_t env_u32(const char *name, uint32_t dflt) {
+    const char *v = getenv(name);
+    return v ? (uint32_t)atoi(v) : dflt;
+}
 
 static int fill_powers(pb200_ctx *ctx, NttPlan *pl, Fr **out, uint32_t count, const Fr *base, uint64_t stride, const Fr *pre) {
     void *buf = nullptr;
@@ -313,6 +339,25 @@ static int ntt_build_plan(pb200_ctx *ctx, uint32_t L, int inverse, int coset, Nt
         PB_TRY(fill_powers(ctx, pl, &clo, 1u << B, c_g, 1, c_one));
         PB_TRY(fill_powers(ctx, pl, &chi, 1u << (L - B), c_g, 1ull << B, inverse ? c_ninv : c_one));
     }
+    // Single-lookup tables replace the two-level composition (one multiply per element instead of two) while
+    // the context's table budget allows: a table is as long as the vector (32·n bytes).
+    const uint32_t full_max_log = env_u32("PB200_NTT_FULL_TABLE_MAX_LOG", 26);
+    const uint32_t tile_pref = std::min(kTileLogMax, std::max(3u, env_u32("PB200_NTT_TILE_LOG", 10)));
+    // CTA tile: the preferred size, but small transforms get smaller tiles so that ≥ 512 CTAs exist
+    auto tile_log_for = [&](uint32_t s_log) { return std::max(s_log, std::min(tile_pref, L >= 9 ? L - 9 : 0u)); };
+    size_t budget_used = 0;
+    for (auto &kv : ctx->ntt_plans) budget_used += kv.second->table_bytes;
+    auto full_ok = [&](uint32_t log_entries) {
+        return L <= full_max_log && budget_used + pl->table_bytes + ((size_t)32 << log_entries) <= ((size_t)16 << 30);
+    };
+    auto alloc_table = [&](uint32_t log_entries, Fr **out) -> int {
+        void *buf = nullptr;
+        PB_CUDA(ctx, cudaMalloc(&buf, (size_t)32 << log_entries));
+        pl->allocs.push_back(buf);
+        pl->table_bytes += (size_t)32 << log_entries;
+        *out = (Fr *)buf;
+        return 0;
+    };
     uint32_t done = 0;  // bits already transformed by earlier passes
     for (int i = 0; i < P; i++) {
         NttPass &p = pl->pass[i];
@@ -325,21 +370,51 @@ static int ntt_build_plan(pb200_ctx *ctx, uint32_t L, int inverse, int coset, Nt
         if (!last) {
             p.type = 0;
             p.ncol_log = L - done - S[i];
-            p.logC = std::min(kTileLogMax - S[i], p.ncol_log);
+            p.logC = std::min(tile_log_for(S[i]) - S[i], p.ncol_log);
             p.store_mode = 2;
             p.mult_log = done;  // ω_m^{j·k} with m = n / 2^done equals ω_n^{(j·k) << done}
             p.s_lo = lo;
             p.s_hi = (i == 0) ? hi_scaled : hi_plain;
             p.s_B = B;
+            if (full_ok(S[i] + p.ncol_log)) {
+                Fr *full = nullptr;
+                PB_TRY(alloc_table(S[i] + p.ncol_log, &full));
+                const uint64_t cnt = 1ull << (S[i] + p.ncol_log);
+                fill_boundary_kernel<<<(uint32_t)((cnt + 255) / 256), 256, 0, ctx->stream>>>(full, S[i], p.ncol_log, p.mult_log,
+                                                                                           p.s_lo, p.s_hi, B);
+                PB_LAUNCHED(ctx);
+                p.store_mode = 4;
+                p.s_full = full;
+            }
         } else {
             p.type = 1;
             p.nrows_log = L - S[i];
             p.n1_log = (P == 3) ? S[0] : p.nrows_log;
-            p.logC = std::min(kTileLogMax - S[i], p.nrows_log);
-            if (inverse && coset) { p.store_mode = 3; p.s_lo = clo; p.s_hi = chi; p.s_B = B; }
+            p.logC = std::min(tile_log_for(S[i]) - S[i], p.nrows_log);
+            if (inverse && coset) {
+                p.store_mode = 3; p.s_lo = clo; p.s_hi = chi; p.s_B = B;
+                if (full_ok(L)) {
+                    Fr *full = nullptr;
+                    PB_TRY(alloc_table(L, &full));
+                    fill_linear_kernel<<<(uint32_t)(((1ull << L) + 255) / 256), 256, 0, ctx->stream>>>(full, L, clo, chi, B);
+                    PB_LAUNCHED(ctx);
+                    p.store_mode = 5;
+                    p.s_full = full;
+                }
+            }
             else if (inverse && P == 1) { p.store_mode = 1; p.s_const = c_ninv; }
         }
-        if (i == 0 && coset && !inverse) { p.load_mode = 1; p.l_lo = clo; p.l_hi = chi; p.l_B = B; }
+        if (i == 0 && coset && !inverse) {
+            p.load_mode = 1; p.l_lo = clo; p.l_hi = chi; p.l_B = B;
+            if (full_ok(L)) {
+                Fr *full = nullptr;
+                PB_TRY(alloc_table(L, &full));
+                fill_linear_kernel<<<(uint32_t)(((1ull << L) + 255) / 256), 256, 0, ctx->stream>>>(full, L, clo, chi, B);
+                PB_LAUNCHED(ctx);
+                p.load_mode = 2;
+                p.l_full = full;
+            }
+        }
         done += S[i];
     }
     return 0;

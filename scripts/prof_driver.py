@@ -14,7 +14,10 @@ ctx = pb.Context(0)
 n = 1 << L
 bases = ctx.malloc(n * 96)
 ctx.synthetic_bases_dev(bases, n)
+PRE = os.environ.get("PRECOMP")
 srs = ctx.srs_wrap_dev(bases, n)
+if PRE:
+    ctx.srs_precompute(srs)
 s = bench.random_fr_limbs(0xB2000000 + L, n)
 sd = ctx.malloc(n * 32)
 ctx.h2d(sd, s)

@@ -22,9 +22,11 @@ ctx.synthetic_bases_dev(bases, 1 << maxl)
 s = bench.random_fr_limbs(0xB2000000 + maxl, 1 << maxl)
 sd = ctx.malloc(32 << maxl)
 ctx.h2d(sd, s)
-for L in sizes:
+for L in ([] if os.environ.get("NTT_ONLY") else sizes):
     n = 1 << L
     srs = ctx.srs_wrap_dev(bases, n)
+    if os.environ.get("PRECOMP") and L <= 22:
+        ctx.srs_precompute(srs)
     for _ in range(2):
         ctx.msm_dev(srs, sd, n)
     ctx.profile_enable(True)
