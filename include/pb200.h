@@ -75,6 +75,22 @@ PB200_API int pb200_ntt(pb200_ctx *ctx, uint64_t *data_host, uint32_t log_n, int
 /* Same transform on a DEVICE-resident vector, in place, ordered on the context stream (no sync). */
 PB200_API int pb200_ntt_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, int inverse, int coset);
 
+/* `batch` independent transforms of 2^log_n scalars each, stored back to back in one device buffer, one launch per
+ * pass for the whole batch (the prover transforms several wire polynomials per round; the sharded transform runs
+ * its rows through this). */
+PB200_API int pb200_ntt_batch_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, uint32_t batch, int inverse, int coset);
+/* Building blocks of the sharded four-step transform for domains ≥ 2^24 spread over G GPUs: one
+ * process per GPU owns a column range of the n1 × (n / n1) view; the host layer (plonk-prototype_b200/dist_ntt.py,
+ * or the Rust shim with NCCL) runs  columns → all-to-all → block transpose → rows (pb200_ntt_dev per row).
+ * pb200_ntt_columns_dev: in-place length-2^log_n1 (i)NTT down every column of the local 2^log_n1 × 2^log_cols
+ * row-major matrix holding global columns [col_offset, col_offset + 2^log_cols), fused with the inter-step twiddle
+ * ω_n^{±col·k} of the 2^log_n transform (forward: after the columns; inverse: before them, plus the 2^-log_n1 scale). */
+PB200_API int pb200_ntt_columns_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, uint32_t log_n1, uint32_t log_cols,
+                                    uint32_t col_offset, int inverse);
+/* dst[(r·blocks + b)·cols + c] = src[(b·rows + r)·cols + c] on 32-byte scalars: regroups what an all-to-all delivered. */
+PB200_API int pb200_block_transpose_dev(pb200_ctx *ctx, uint64_t *dst_dev, const uint64_t *src_dev, uint32_t blocks,
+                                        uint32_t rows, uint32_t cols);
+
 /* ---- MSM: dusk_bls12_381::multiscalar_mul::msm_variable_base ---- */
 /* Upload bases once (CommitKey::powers_of_g); they stay resident for every later commit. */
 PB200_API int pb200_srs_upload(pb200_ctx *ctx, const uint64_t *xy_mont_host, size_t n_points, pb200_srs **out);

@@ -15,7 +15,7 @@ _lib = None
 EXPORTS = [
     "pb200_init", "pb200_destroy", "pb200_last_error", "pb200_stream", "pb200_sync",
     "pb200_malloc", "pb200_free", "pb200_h2d", "pb200_d2h",
-    "pb200_domain_log_size", "pb200_ntt", "pb200_ntt_dev",
+    "pb200_domain_log_size", "pb200_ntt", "pb200_ntt_dev", "pb200_ntt_batch_dev", "pb200_ntt_columns_dev", "pb200_block_transpose_dev",
     "pb200_srs_upload", "pb200_srs_wrap_dev", "pb200_srs_precompute", "pb200_srs_free", "pb200_srs_len",
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_g1_sum", "pb200_msm_window_bits",
     "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_launch_count",
@@ -50,6 +50,9 @@ def lib():
         L.pb200_domain_log_size.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)]
         L.pb200_ntt.argtypes = [vp, u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
         L.pb200_ntt_dev.argtypes = [vp, u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
+        L.pb200_ntt_batch_dev.argtypes = [vp, u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
+        L.pb200_ntt_columns_dev.argtypes = [vp, u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
+        L.pb200_block_transpose_dev.argtypes = [vp, u64p, u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
         L.pb200_srs_upload.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.POINTER(vp)]
         L.pb200_srs_wrap_dev.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.POINTER(vp)]
         L.pb200_srs_precompute.argtypes = [vp, vp]
@@ -138,6 +141,15 @@ class Context:
 
     def ntt_dev(self, dev, log_n, inverse=False, coset=False):
         self._check(lib().pb200_ntt_dev(self._h, ctypes.c_void_p(dev), log_n, int(inverse), int(coset)))
+
+    def ntt_batch_dev(self, dev, log_n, batch, inverse=False, coset=False):
+        self._check(lib().pb200_ntt_batch_dev(self._h, ctypes.c_void_p(dev), log_n, batch, int(inverse), int(coset)))
+
+    def ntt_columns_dev(self, dev, log_n, log_n1, log_cols, col_offset, inverse=False):
+        self._check(lib().pb200_ntt_columns_dev(self._h, ctypes.c_void_p(dev), log_n, log_n1, log_cols, col_offset, int(inverse)))
+
+    def block_transpose_dev(self, dst, src, blocks, rows, cols):
+        self._check(lib().pb200_block_transpose_dev(self._h, ctypes.c_void_p(dst), ctypes.c_void_p(src), blocks, rows, cols))
 
     # -- MSM
     def srs_upload(self, xy_host):

@@ -19,10 +19,13 @@ __global__ void __launch_bounds__(128) msm_accumulate_slots_kernel(const uint32_
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_in = *n_in_ptr;
     if (t == 0) *n_out_ptr = 2 * (uint32_t)(((uint64_t)n_in + L - 1) / L);
-    const uint64_t start64 = (uint64_t)t * L;
+    // Segments start at odd slots: the two partials of a bucket that straddled one boundary of the previous level
+    // sit at slots (2u+1, 2u+2), so an odd-aligned segmentation never splits such a pair and one level finishes
+    // every bucket that is not heavy.  Slot 0 (the head slot of thread 0) is always a hole.
+    const uint64_t start64 = (uint64_t)t * L + 1;
     if (start64 >= n_in) return;
     const uint32_t start = (uint32_t)start64, end = (uint32_t)min((uint64_t)n_in, start64 + L);
-    const uint32_t prev = start > 0 ? in_gb[start - 1] : kInvalid;
+    const uint32_t prev = in_gb[start - 1];
     const uint32_t next = end < n_in ? in_gb[end] : kInvalid;
     RunSink sink{buckets, out_gb, out_pt, t, kInvalid, kInvalid};
 

@@ -30,9 +30,12 @@ struct NttPass {
     uint32_t nrows_log;  // type 1: log2(number of rows) = log n − S
     uint32_t n1_log;     // type 1: log2 of the first-pass length (row ↔ natural-index digit swap)
     uint32_t load_mode;  // 0 none | 1 × lo[e]·hi[e], e = natural input index | 2 × full[e]           (coset_fft)
+                         // 3 × pow((col_offset + col)·x << mult_log)  (type 0: inverse four-step twiddle before the columns)
     uint32_t store_mode; // 0 none | 1 × constant | 2 × pow(col·k << mult_log) | 3 × pow(natural output index)
                          // 4 × full[(k << ncol_log) + col] (inter-pass twiddle, one lookup) | 5 × full[natural output index]
     uint32_t mult_log;
+    uint32_t col_offset; // global index of local column 0 (sharded four-step: this rank owns a column range)
+    uint32_t batch_log;  // blockIdx.y selects one of several independent vectors of 2^batch_log scalars each
     uint32_t l_B, s_B;   // split point of the two-level power tables
     const Fr *tw;        // ω_{2^S}^j, j < 2^(S−1)
     const Fr *l_lo, *l_hi, *s_lo, *s_hi;
@@ -86,6 +89,8 @@ __device__ __forceinline__ void bfly1(Fr &a, Fr &b) {  // w = 1
 
 __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const Fr *__restrict__ in, Fr *__restrict__ out, NttPass p) {
     extern __shared__ uint32_t sm[];
+    in += (uint64_t)blockIdx.y << p.batch_log;
+    out += (uint64_t)blockIdx.y << p.batch_log;
     const uint32_t S = p.S, logC = p.logC, C = 1u << logC;
     const uint32_t T = 1u << (S + logC), PS = T + (T >> 5) + 1;
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
@@ -123,6 +128,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const Fr *__restrict__
         Fr v = g_load(in + addr);
         if (p.load_mode == 1) v = v * pow2level(p.l_lo, p.l_hi, p.l_B, (uint32_t)addr);
         else if (p.load_mode == 2) v = v * g_load(p.l_full + addr);
+        else if (p.load_mode == 3) v = v * pow2level(p.l_lo, p.l_hi, p.l_B, ((p.col_offset + col0 + c) * x) << p.mult_log);
         sm_store(sm, PS, (x << logC) + c, v);
     }
     __syncthreads();
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const Fr *__restrict__
         uint64_t addr;
         if (p.type == 0) {
             addr = in_base + ((uint64_t)k << p.ncol_log) + c;
-            if (p.store_mode == 2) v = v * pow2level(p.s_lo, p.s_hi, p.s_B, ((col0 + c) * k) << p.mult_log);
+            if (p.store_mode == 2) v = v * pow2level(p.s_lo, p.s_hi, p.s_B, ((p.col_offset + col0 + c) * k) << p.mult_log);
             else if (p.store_mode == 4) v = v * g_load(p.s_full + (((uint64_t)k << p.ncol_log) + col0 + c));
         } else {
             addr = (uint64_t)(rowrev0 + c) + ((uint64_t)k << p.nrows_log);
@@ -275,6 +281,17 @@ __global__ void fill_linear_kernel(Fr *out, uint32_t L, const Fr *lo, const Fr *
     const uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= (1ull << L)) return;
     g_store(out + i, pow2level(lo, hi, B, (uint32_t)i));
+}
+
+// out[(r·B + b)·C + c] = in[(b·R + r)·C + c]: regroups the G received blocks of an all-to-all ([B][R][C] → [R][B][C]).
+__global__ void block_transpose_kernel(Fr *__restrict__ out, const Fr *__restrict__ in, uint32_t B, uint32_t R, uint32_t C) {
+    const uint64_t total = (uint64_t)B * R * C;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i % C);
+        const uint64_t br = i / C;
+        const uint32_t r = (uint32_t)(br % R), b = (uint32_t)(br / R);
+        g_store(out + ((uint64_t)r * B + b) * C + c, g_load(in + i));
+    }
 }
 
 }  // namespace
@@ -431,7 +448,7 @@ void ntt_free_plans(pb200_ctx *ctx) {
     ctx->ntt_scratch_bytes = 0;
 }
 
-static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset) {
+static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset, uint32_t batch = 1) {
     if (L == 0) return 0;  // a one-point domain: every variant is the identity map
     NttPlan *pl = nullptr;
     auto it = ctx->ntt_plans.find(L | ((uint32_t)inverse << 8) | ((uint32_t)coset << 9));
@@ -439,10 +456,12 @@ static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset)
     else PB_TRY(ntt_build_plan(ctx, L, inverse, coset, &pl));
     PbTimer timer(ctx, "ntt.total");
     if (pl->n_pass == 0) {
-        ntt_tiny_kernel<<<1, 1, 0, ctx->stream>>>(data, L, inverse, coset, pl->consts);
-        PB_LAUNCHED(ctx);
+        for (uint32_t b = 0; b < batch; b++) {
+            ntt_tiny_kernel<<<1, 1, 0, ctx->stream>>>(data + ((size_t)b << L), L, inverse, coset, pl->consts);
+            PB_LAUNCHED(ctx);
+        }
     } else {
-        const size_t bytes = sizeof(Fr) << L;
+        const size_t bytes = (sizeof(Fr) << L) * batch;
         Fr *scratch = nullptr;
         if (pl->n_pass > 1) {
             PB_TRY(pb_ensure(ctx, &ctx->ntt_scratch, &ctx->ntt_scratch_bytes, bytes));
@@ -457,8 +476,13 @@ static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset)
             // pass 0 reads the caller's vector, the last pass writes it; intermediates live in scratch
             const Fr *src = (i == 0) ? data : scratch;
             Fr *dst = (i == pl->n_pass - 1) ? data : scratch;
-            ntt_pass_kernel<<<blocks, threads, smem, ctx->stream>>>(src, dst, p);
-            PB_LAUNCHED(ctx);
+            NttPass pb = p;
+            pb.batch_log = L;
+            for (uint32_t b0 = 0; b0 < batch; b0 += 32768) {  // gridDim.y ≤ 65535
+                const uint32_t nb = std::min<uint32_t>(32768, batch - b0);
+                ntt_pass_kernel<<<dim3(blocks, nb), threads, smem, ctx->stream>>>(src + ((size_t)b0 << L), dst + ((size_t)b0 << L), pb);
+                PB_LAUNCHED(ctx);
+            }
         }
     }
     timer.stop();
@@ -490,6 +514,13 @@ extern "C" int pb200_ntt_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n,
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     return ntt_run(ctx, (Fr *)data_dev, log_n, inverse ? 1 : 0, coset ? 1 : 0);
 }
+extern "C" int pb200_ntt_batch_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, uint32_t batch, int inverse, int coset) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, data_dev != nullptr);
+    PB_ARG(ctx, log_n < kTwoAdicity && batch >= 1);
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    return ntt_run(ctx, (Fr *)data_dev, log_n, inverse ? 1 : 0, coset ? 1 : 0, batch);
+}
 extern "C" int pb200_ntt(pb200_ctx *ctx, uint64_t *data_host, uint32_t log_n, int inverse, int coset) {
     if (!ctx) return PB200_ERR_ARG;
     PB_ARG(ctx, data_host != nullptr);
@@ -501,5 +532,83 @@ extern "C" int pb200_ntt(pb200_ctx *ctx, uint64_t *data_host, uint32_t log_n, in
     PB_TRY(ntt_run(ctx, (Fr *)ctx->stage, log_n, inverse ? 1 : 0, coset ? 1 : 0));
     PB_CUDA(ctx, cudaMemcpyAsync(data_host, ctx->stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- sharded four-step building blocks (orchestrated by plonk-prototype_b200/dist_ntt.py) ----------
+// Column step of a 2^log_n transform split as n = n1·m over G ranks: this rank holds the n1 × cols matrix of its
+// column range [col_offset, col_offset + cols) (row-major, cols = 2^log_cols).
+//   forward: length-n1 NTT down every column, then × ω_n^{(col_offset + col)·k1}          (before the all-to-all)
+//   inverse: × ω_n^{−(col_offset + col)·k1}, then length-n1 iNTT down every column, × n1⁻¹  (after the all-to-all back)
+// One pass, in place; log_n1 ≤ 11.
+extern "C" int pb200_ntt_columns_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, uint32_t log_n1, uint32_t log_cols,
+                                     uint32_t col_offset, int inverse) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, data_dev != nullptr);
+    PB_ARG(ctx, log_n < kTwoAdicity && log_n1 >= 3 && log_n1 <= kTileLogMax && log_n1 + log_cols <= log_n);
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    inverse = inverse ? 1 : 0;
+    const uint32_t key = 0x40000000u | log_n | (log_n1 << 8) | ((uint32_t)inverse << 16);
+    NttPlan *pl = nullptr;
+    auto it = ctx->ntt_plans.find(key);
+    if (it != ctx->ntt_plans.end()) {
+        pl = it->second;
+    } else {
+        pl = new NttPlan();
+        pl->log_n = log_n;
+        pl->inverse = inverse;
+        ctx->ntt_plans[key] = pl;
+        void *cbuf = nullptr;
+        PB_CUDA(ctx, cudaMalloc(&cbuf, 5 * sizeof(Fr)));
+        pl->allocs.push_back(cbuf);
+        pl->consts = (Fr *)cbuf;
+        ntt_consts_kernel<<<1, 1, 0, ctx->stream>>>(pl->consts, log_n, inverse);
+        PB_LAUNCHED(ctx);
+        const Fr *c_w = pl->consts + 0, *c_one = pl->consts + 3;
+        // n1⁻¹ = (2⁻¹)^log_n1: consts[1] holds 2^−log_n; reuse the constants kernel for a 2^log_n1 domain
+        Fr *c1 = nullptr;
+        void *c1buf = nullptr;
+        PB_CUDA(ctx, cudaMalloc(&c1buf, 4 * sizeof(Fr)));
+        pl->allocs.push_back(c1buf);
+        c1 = (Fr *)c1buf;
+        ntt_consts_kernel<<<1, 1, 0, ctx->stream>>>(c1, log_n1, inverse);
+        PB_LAUNCHED(ctx);
+        const uint32_t B = (log_n + 1) / 2;
+        Fr *lo = nullptr, *hi = nullptr, *tw = nullptr;
+        PB_TRY(fill_powers(ctx, pl, &lo, 1u << B, c_w, 1, c_one));
+        PB_TRY(fill_powers(ctx, pl, &hi, 1u << (log_n - B), c_w, 1ull << B, c_one));
+        PB_TRY(fill_powers(ctx, pl, &tw, 1u << (log_n1 - 1), c_w, 1ull << (log_n - log_n1), c_one));
+        NttPass &p = pl->pass[0];
+        memset(&p, 0, sizeof(p));
+        p.S = log_n1;
+        p.type = 0;
+        p.tw = tw;
+        if (!inverse) { p.store_mode = 2; p.s_lo = lo; p.s_hi = hi; p.s_B = B; }
+        else { p.load_mode = 3; p.l_lo = lo; p.l_hi = hi; p.l_B = B; p.store_mode = 1; p.s_const = c1 + 1; }
+        pl->n_pass = 1;
+    }
+    NttPass p = pl->pass[0];
+    p.ncol_log = log_cols;
+    p.col_offset = col_offset;
+    p.mult_log = 0;  // the twiddle is ω_n^{j'·k1} with j' the global column index in [0, n / n1)
+    const uint32_t tile_log = std::max(log_n1, std::min(10u, log_n1 + log_cols));
+    p.logC = std::min(tile_log - log_n1, log_cols);
+    const uint32_t T = 1u << (p.S + p.logC);
+    const size_t smem = (size_t)8 * (T + (T >> 5) + 1) * sizeof(uint32_t);
+    const uint32_t blocks = 1u << (log_cols - p.logC);
+    ntt_pass_kernel<<<blocks, T >> 3, smem, ctx->stream>>>((const Fr *)data_dev, (Fr *)data_dev, p);
+    PB_LAUNCHED(ctx);
+    return 0;
+}
+extern "C" int pb200_block_transpose_dev(pb200_ctx *ctx, uint64_t *dst_dev, const uint64_t *src_dev, uint32_t blocks, uint32_t rows,
+                                         uint32_t cols) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, dst_dev != nullptr && src_dev != nullptr && dst_dev != src_dev);
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t total = (uint64_t)blocks * rows * cols;
+    if (total == 0) return 0;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->sm_count * 32);
+    block_transpose_kernel<<<grid, 256, 0, ctx->stream>>>((Fr *)dst_dev, (const Fr *)src_dev, blocks, rows, cols);
+    PB_LAUNCHED(ctx);
     return 0;
 }

@@ -121,3 +121,20 @@ def test_invalid_domain_is_an_error(ctx):
     import plonk_prototype_b200 as pb
     with pytest.raises(pb.Pb200Error):
         ctx.ntt_dev(ctx.malloc(32), 32, 0, 0)
+
+
+@pytest.mark.parametrize("log_n,batch", [(1, 3), (5, 7), (11, 4), (13, 5), (16, 3)])
+def test_batched_transforms_match_single(ctx, oracle, log_n, batch):
+    n = 1 << log_n
+    x = oracle.fr_to_mont(oracle.random_fr(0xBA7C + log_n, n * batch))
+    d = ctx.malloc(x.nbytes)
+    try:
+        for name, inv, cos in VARIANTS:
+            ctx.h2d(d, x)
+            ctx.ntt_batch_dev(d, log_n, batch, inv, cos)
+            got = np.empty_like(x)
+            ctx.d2h(got, d)
+            for b in range(batch):
+                assert (got[b * n:(b + 1) * n] == oracle.ntt(x[b * n:(b + 1) * n], inv, cos, threads=4)).all(), (name, b)
+    finally:
+        ctx.free(d)
