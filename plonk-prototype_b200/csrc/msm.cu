@@ -52,15 +52,36 @@ __global__ void __launch_bounds__(256) msm_count_kernel(const uint64_t *scalars,
         });
     }
 }
-__global__ void __launch_bounds__(256) msm_scatter_kernel(const uint64_t *scalars, MsmCfg cfg, uint32_t *cursor, uint2 *entries) {
+// `shift` = 0: entries go straight to their bucket's slot range (cursor = per-bucket offsets).
+// `shift` > 0: first level of the two-level scatter — the cursor array is per *coarse bin* (2^shift buckets) and
+// entries are only grouped by bin; msm_fine_scatter_kernel finishes the job.
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const uint64_t *scalars, MsmCfg cfg, uint32_t *cursor, uint2 *entries,
+                                                          uint32_t shift) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cfg.n; i += (size_t)gridDim.x * blockDim.x) {
         Fr s = load_fr(scalars, i).from_mont();
         for_each_digit(s, cfg.c, cfg.W, [&](uint32_t w, uint32_t mag, uint32_t sign) {
             const uint32_t gb = (cfg.pre_stride ? 0u : (w << cfg.nb_log)) + mag - 1;
-            const uint32_t pos = atomicAdd(&cursor[gb], 1u);
+            const uint32_t pos = atomicAdd(&cursor[gb >> shift], 1u);
             entries[pos] = make_uint2(gb, (uint32_t)(w * cfg.pre_stride + i) | (sign << 31));
         });
     }
+}
+// coarse[b] = offsets[b << shift]: where each coarse bin starts in the entry list
+__global__ void msm_coarse_init_kernel(const uint32_t *offsets, uint32_t *coarse, uint32_t n_coarse, uint32_t shift) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_coarse) coarse[b] = offsets[b << shift];
+}
+// Second level: walk the bin-grouped list in order; each entry moves to its bucket's slot.  CTAs that run at the
+// same time cover a few neighbouring bins, so the scattered 8-byte writes stay inside an L2-resident window and
+// reach DRAM as full lines (the single-level scatter wrote one 32-byte sector per entry all over a 6 GB array).
+__global__ void __launch_bounds__(256) msm_fine_scatter_kernel(const uint2 *__restrict__ grouped, const uint32_t *__restrict__ n_entries_ptr,
+                                                               uint32_t *cursor, uint2 *entries) {
+    const uint32_t M = *n_entries_ptr;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const uint2 e = grouped[i];
+    const uint32_t pos = atomicAdd(&cursor[e.x], 1u);
+    entries[pos] = e;
 }
 
 // ------------------------------------------------------------------------------------------- scan
@@ -246,6 +267,14 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     const size_t o_count = carve((size_t)TB * 4), o_cursor = carve((size_t)TB * 4), o_bsum = carve((size_t)n_scan_blocks * 4);
     const size_t o_meta = carve(64 * 4);
     const size_t o_entries = carve((size_t)m0 * 8);
+    // two-level scatter once the entry list outgrows L2: coarse bins of ~32 Ki entries, never crossing a window
+    uint32_t coarse_shift = 0;
+    if (m0 * 8 > ((size_t)1 << 30)) {
+        const double per_bucket = std::max(1.0, (double)m0 / (double)TB);
+        while (coarse_shift < cfg.nb_log && per_bucket * (double)(2u << coarse_shift) <= 32768.0) coarse_shift++;
+    }
+    const uint32_t n_coarse = coarse_shift ? (TB >> coarse_shift) : 0;
+    const size_t o_grouped = carve(coarse_shift ? (size_t)m0 * 8 : 0), o_coarse = carve((size_t)n_coarse * 4);
     const size_t o_buckets = carve((size_t)TB * sizeof(G1Xyzz));
     const size_t slotsA = lvl_slots[0], slotsB = lvl_slots.size() > 1 ? lvl_slots[1] : 2;
     const size_t o_gbA = carve(slotsA * 4), o_ptA = carve(slotsA * sizeof(G1Xyzz));
@@ -258,7 +287,8 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     char *ws = (char *)ctx->msm_ws;
     uint32_t *count = (uint32_t *)(ws + o_count), *cursor = (uint32_t *)(ws + o_cursor), *bsum = (uint32_t *)(ws + o_bsum);
     uint32_t *meta = (uint32_t *)(ws + o_meta);  // [0] = #entries, [1+k] = #slots produced by level k
-    uint2 *entries = (uint2 *)(ws + o_entries);
+    uint2 *entries = (uint2 *)(ws + o_entries), *grouped = (uint2 *)(ws + o_grouped);
+    uint32_t *coarse = (uint32_t *)(ws + o_coarse);
     G1Xyzz *buckets = (G1Xyzz *)(ws + o_buckets);
     uint32_t *gbA = (uint32_t *)(ws + o_gbA), *gbB = (uint32_t *)(ws + o_gbB);
     G1Xyzz *ptA = (G1Xyzz *)(ws + o_ptA), *ptB = (G1Xyzz *)(ws + o_ptB);
@@ -276,7 +306,15 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     PB_LAUNCHED(ctx);
     scan_apply_kernel<<<n_scan_blocks, kScanThreads, 0, st>>>(count, TB, bsum, cursor);
     PB_LAUNCHED(ctx);
-    msm_scatter_kernel<<<sgrid, 256, 0, st>>>(scalars, cfg, cursor, entries);
+    if (coarse_shift) {
+        msm_coarse_init_kernel<<<(n_coarse + 255) / 256, 256, 0, st>>>(cursor, coarse, n_coarse, coarse_shift);
+        PB_LAUNCHED(ctx);
+        msm_scatter_kernel<<<sgrid, 256, 0, st>>>(scalars, cfg, coarse, grouped, coarse_shift);
+        PB_LAUNCHED(ctx);
+        msm_fine_scatter_kernel<<<(uint32_t)((m0 + 255) / 256), 256, 0, st>>>(grouped, meta + 0, cursor, entries);
+    } else {
+        msm_scatter_kernel<<<sgrid, 256, 0, st>>>(scalars, cfg, cursor, entries, 0);
+    }
     PB_LAUNCHED(ctx);
     t_sort.stop();
 

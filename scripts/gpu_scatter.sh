@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_msm_gpu.py -x -q -m gpu 2>&1 | tail -3
+SIZES=22,24,26 python scripts/sweep.py 2>&1 >/dev/null | grep mpts | cut -c1-330
