@@ -11,6 +11,7 @@
  */
 #include <stdint.h>
 #include <string.h>
+#include "mont_asm.h"
 
 #ifndef MF_CAT
 #define MF_CAT_(a, b) a##_##b
@@ -81,6 +82,10 @@ static inline void MF(dbl)(MF(t) *o, const MF(t) *a) { MF(add)(o, a, a); }
 /* Montgomery product o = a·b·R⁻¹ mod MOD, fully reduced: schoolbook 2N-limb product followed by
  * N word-by-word reduction rounds (the product-then-`montgomery_reduce` shape dusk-bls12_381 uses). */
 static inline void MF(mul)(MF(t) *o, const MF(t) *a, const MF(t) *b) {
+#if defined(ORC_HAVE_MONT_ASM) && !defined(ORC_NO_ASM)
+    if (MF_N == 4) { orc_mont_mul4_asm(o->l, a->l, b->l, MF(MOD).l, MF(INV)); return; }
+    if (MF_N == 6) { orc_mont_mul6_asm(o->l, a->l, b->l, MF(MOD).l, MF(INV)); return; }
+#endif
     uint64_t t[2 * MF_N];
     {
         u128 c = 0;

@@ -17,7 +17,7 @@ _U64P = ctypes.POINTER(ctypes.c_uint64)
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    src = [os.path.join(_HERE, f) for f in ("oracle.c", "mont.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("oracle.c", "mont.h", "mont_asm.h", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return so
