@@ -56,16 +56,20 @@ __device__ __forceinline__ void g_store(Fr *p, const Fr &v) {
     q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
     q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
-// Shared-memory tile: 8 limb planes of PS words; element i lives at word i + (i >> 5) of each plane.
+// Shared-memory tile: 8 limb planes of PS words; element i lives at word i ^ ((i >> 3) & 31) of each plane.
+// In a round on bits [b_lo, b_lo+2] the 32 lanes of a warp cover the low L0 = logC + b_lo index bits and, when
+// L0 < 5, the bits from L0+3 upward; bank bit k = i_k ^ i_(k+3) is a bijection of the lane bits for every L0
+// (checked case by case in DESIGN.md §4.2), so every access pattern of the kernel is bank-conflict free.
+__device__ __forceinline__ uint32_t sm_slot(uint32_t i) { return i ^ ((i >> 3) & 31u); }
 __device__ __forceinline__ Fr sm_load(const uint32_t *sm, uint32_t PS, uint32_t i) {
-    uint32_t s = i + (i >> 5);
+    uint32_t s = sm_slot(i);
     Fr r;
 #pragma unroll
     for (int w = 0; w < 8; w++) r.l[w] = sm[w * PS + s];
     return r;
 }
 __device__ __forceinline__ void sm_store(uint32_t *sm, uint32_t PS, uint32_t i, const Fr &v) {
-    uint32_t s = i + (i >> 5);
+    uint32_t s = sm_slot(i);
 #pragma unroll
     for (int w = 0; w < 8; w++) sm[w * PS + s] = v.l[w];
 }
@@ -87,18 +91,65 @@ __device__ __forceinline__ void bfly1(Fr &a, Fr &b) {  // w = 1
     a = s;
 }
 
+// Three DIF stages on bits [b_lo, b_lo+2] (b_lo ≥ 1) of the eight points a thread holds; v = x mod 2^b_lo.
+__device__ __forceinline__ void radix8_general(Fr (&a)[8], const Fr *tw, uint32_t v, uint32_t b_lo, uint32_t S) {
+    {
+        const uint32_t sh = S - 3 - b_lo;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            Fr w = g_load(tw + ((((uint32_t)e << b_lo) | v) << sh));
+            bfly(a[e], a[e + 4], w);
+        }
+    }
+    {
+        const uint32_t sh = S - 2 - b_lo;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            Fr w = g_load(tw + ((((uint32_t)e << b_lo) | v) << sh));
+            bfly(a[e], a[e + 2], w);
+            bfly(a[e + 4], a[e + 6], w);
+        }
+    }
+    {
+        Fr w = g_load(tw + (v << (S - 1 - b_lo)));
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) bfly(a[e], a[e + 1], w);
+    }
+}
+// The last round, on bits [0, 2]: only stages b_top … 0 remain and their twiddles are the constants ω₈^k.
+__device__ __forceinline__ void radix8_low(Fr (&a)[8], const Fr *tw, int b_top, uint32_t S) {
+    if (b_top >= 2) {
+        bfly1(a[0], a[4]);
+#pragma unroll
+        for (int e = 1; e < 4; e++) {
+            Fr w = g_load(tw + ((uint32_t)e << (S - 3)));
+            bfly(a[e], a[e + 4], w);
+        }
+    }
+    if (b_top >= 1) {
+        Fr w4 = g_load(tw + (1u << (S - 2)));
+        bfly1(a[0], a[2]);
+        bfly1(a[4], a[6]);
+        bfly(a[1], a[3], w4);
+        bfly(a[5], a[7], w4);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; e += 2) bfly1(a[e], a[e + 1]);
+}
+
+// One pass: stage the tile global → shared (coalesced, optional input scaling), run every round through shared
+// memory, then shared → global with the bit reversal, twiddle and scalings.  (A variant that fed the first round
+// straight from global memory and stored from the last round's registers measured 8-25 % slower on B200 — the extra
+// live registers cost more than the two saved exchanges — and was dropped.)
 __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const Fr *__restrict__ in, Fr *__restrict__ out, NttPass p) {
     extern __shared__ uint32_t sm[];
     in += (uint64_t)blockIdx.y << p.batch_log;
     out += (uint64_t)blockIdx.y << p.batch_log;
     const uint32_t S = p.S, logC = p.logC, C = 1u << logC;
-    const uint32_t T = 1u << (S + logC), PS = T + (T >> 5) + 1;
+    const uint32_t T = 1u << (S + logC), PS = max(T, 32u);
     const uint32_t tid = threadIdx.x, nthr = blockDim.x;
-
-    // ---- tile geometry
-    uint64_t in_base;       // address of (x = 0, c = 0)
-    uint32_t rowrev0 = 0;   // type 1: natural-order row digit of column 0
-    uint32_t col0 = 0;      // type 0: column index of c = 0 inside its row block
+    uint64_t in_base = 0;
+    uint32_t rowrev0 = 0, col0 = 0;
     if (p.type == 0) {
         uint32_t blocks_per_row_log = p.ncol_log - logC;
         uint32_t R = blockIdx.x >> blocks_per_row_log;
@@ -106,11 +157,8 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const Fr *__restrict__
         in_base = ((uint64_t)R << (S + p.ncol_log)) + col0;
     } else {
         rowrev0 = blockIdx.x << logC;
-        in_base = 0;
     }
     const uint32_t n2_log = p.nrows_log - p.n1_log;
-
-    // ---- phase 1: global → shared (coalesced along the contiguous axis), optional coset scaling
     for (uint32_t i = tid; i < T; i += nthr) {
         uint32_t x, c;
         uint64_t addr;
@@ -132,74 +180,29 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const Fr *__restrict__
         sm_store(sm, PS, (x << logC) + c, v);
     }
     __syncthreads();
-
-    // ---- phase 2: S DIF stages, three per round, eight points per thread
     {
         const uint32_t c = tid & (C - 1), tx = tid >> logC;
         int b_top = (int)S - 1;
-        while (b_top >= 3) {  // general round on bits [b_lo, b_lo+2], b_lo ≥ 1
+        Fr a[8];
+        while (b_top >= 3) {
             const uint32_t b_lo = (uint32_t)b_top - 2;
             const uint32_t v = tx & ((1u << b_lo) - 1), u = tx >> b_lo;
             const uint32_t xbase = (u << (b_lo + 3)) | v;
-            Fr a[8];
 #pragma unroll
             for (int e = 0; e < 8; e++) a[e] = sm_load(sm, PS, ((xbase | ((uint32_t)e << b_lo)) << logC) + c);
-            {
-                const uint32_t sh = S - 3 - b_lo;
-#pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    Fr w = g_load(p.tw + ((((uint32_t)e << b_lo) | v) << sh));
-                    bfly(a[e], a[e + 4], w);
-                }
-            }
-            {
-                const uint32_t sh = S - 2 - b_lo;
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    Fr w = g_load(p.tw + ((((uint32_t)e << b_lo) | v) << sh));
-                    bfly(a[e], a[e + 2], w);
-                    bfly(a[e + 4], a[e + 6], w);
-                }
-            }
-            {
-                Fr w = g_load(p.tw + (v << (S - 1 - b_lo)));
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) bfly(a[e], a[e + 1], w);
-            }
+            radix8_general(a, p.tw, v, b_lo, S);
 #pragma unroll
             for (int e = 0; e < 8; e++) sm_store(sm, PS, ((xbase | ((uint32_t)e << b_lo)) << logC) + c, a[e]);
             __syncthreads();
             b_top -= 3;
         }
-        {  // last round on bits [0, 2]: only stages b_top … 0 remain and their twiddles are constants
-            const uint32_t xbase = tx << 3;
-            Fr a[8];
 #pragma unroll
-            for (int e = 0; e < 8; e++) a[e] = sm_load(sm, PS, ((xbase | (uint32_t)e) << logC) + c);
-            if (b_top >= 2) {
-                bfly1(a[0], a[4]);
+        for (int e = 0; e < 8; e++) a[e] = sm_load(sm, PS, (((tx << 3) | (uint32_t)e) << logC) + c);
+        radix8_low(a, p.tw, b_top, S);
 #pragma unroll
-                for (int e = 1; e < 4; e++) {
-                    Fr w = g_load(p.tw + ((uint32_t)e << (S - 3)));
-                    bfly(a[e], a[e + 4], w);
-                }
-            }
-            if (b_top >= 1) {
-                Fr w4 = g_load(p.tw + (1u << (S - 2)));
-                bfly1(a[0], a[2]);
-                bfly1(a[4], a[6]);
-                bfly(a[1], a[3], w4);
-                bfly(a[5], a[7], w4);
-            }
-#pragma unroll
-            for (int e = 0; e < 8; e += 2) bfly1(a[e], a[e + 1]);
-#pragma unroll
-            for (int e = 0; e < 8; e++) sm_store(sm, PS, ((xbase | (uint32_t)e) << logC) + c, a[e]);
-            __syncthreads();
-        }
+        for (int e = 0; e < 8; e++) sm_store(sm, PS, (((tx << 3) | (uint32_t)e) << logC) + c, a[e]);
+        __syncthreads();
     }
-
-    // ---- phase 3: shared → global; position x holds output index k = bitrev_S(x)
     for (uint32_t i = tid; i < T; i += nthr) {
         const uint32_t c = i & (C - 1), x = i >> logC;
         const uint32_t k = __brev(x) >> (32 - S);
@@ -471,7 +474,7 @@ static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset,
             const NttPass &p = pl->pass[i];
             const uint32_t tile_log = p.S + p.logC;
             const uint32_t T = 1u << tile_log;
-            const size_t smem = (size_t)8 * (T + (T >> 5) + 1) * sizeof(uint32_t);
+            const size_t smem = (size_t)8 * std::max(T, 32u) * sizeof(uint32_t);
             const uint32_t threads = T >> 3, blocks = 1u << (L - tile_log);
             // pass 0 reads the caller's vector, the last pass writes it; intermediates live in scratch
             const Fr *src = (i == 0) ? data : scratch;
@@ -495,7 +498,7 @@ static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset,
 
 int ntt_module_init(pb200_ctx *ctx) {
     PB_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      8 * ((1 << kTileLogMax) + (1 << (kTileLogMax - 5)) + 1) * 4));
+                                      8 * (1 << kTileLogMax) * 4));
     return 0;
 }
 
@@ -594,7 +597,7 @@ extern "C" int pb200_ntt_columns_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_
     const uint32_t tile_log = std::max(log_n1, std::min(10u, log_n1 + log_cols));
     p.logC = std::min(tile_log - log_n1, log_cols);
     const uint32_t T = 1u << (p.S + p.logC);
-    const size_t smem = (size_t)8 * (T + (T >> 5) + 1) * sizeof(uint32_t);
+    const size_t smem = (size_t)8 * std::max(T, 32u) * sizeof(uint32_t);
     const uint32_t blocks = 1u << (log_cols - p.logC);
     ntt_pass_kernel<<<blocks, T >> 3, smem, ctx->stream>>>((const Fr *)data_dev, (Fr *)data_dev, p);
     PB_LAUNCHED(ctx);
