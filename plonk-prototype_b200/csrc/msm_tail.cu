@@ -18,7 +18,8 @@ __global__ void __launch_bounds__(128) msm_accumulate_slots_kernel(const uint32_
                                                                    uint32_t *n_out_ptr) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_in = *n_in_ptr;
-    if (t == 0) *n_out_ptr = 2 * (uint32_t)(((uint64_t)n_in + L - 1) / L);
+    // thread u runs iff u·L + 1 < n_in, so exactly ceil((n_in − 1) / L) threads write their two output slots
+    if (t == 0) *n_out_ptr = n_in > 1 ? 2 * (uint32_t)(((uint64_t)n_in - 1 + L - 1) / L) : 0;
     // Segments start at odd slots: the two partials of a bucket that straddled one boundary of the previous level
     // sit at slots (2u+1, 2u+2), so an odd-aligned segmentation never splits such a pair and one level finishes
     // every bucket that is not heavy.  Slot 0 (the head slot of thread 0) is always a hole.

@@ -205,3 +205,23 @@ def test_precomputed_equal_bases(ctx, oracle):
         assert aff(oracle, ctx.msm(srs, s)) == aff(oracle, oracle.msm_variable_base(same, s, threads=8))
     finally:
         ctx.srs_free(srs)
+
+
+def test_many_sizes_closed_form(ctx, oracle):
+    """Boundary sizes (segment / level / window edges) with and without pre-doubled copies, checked exactly."""
+    nmax = 5000
+    pts = oracle.synthetic_bases(nmax)
+    srs_plain = ctx.srs_upload(pts)
+    srs_pre = ctx.srs_upload(pts)
+    ctx.srs_precompute(srs_pre)
+    s_all = oracle.random_fr(0x51CE, nmax)
+    try:
+        sizes = list(range(1, 40)) + [63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 513, 1000, 1023, 1025, 2047, 2049,
+                                      3001, 4095, 4097, 4999, 5000]
+        for n in sizes:
+            want = model.g1_mul(model.G1_GEN, closed_form_msm_scalar(s_all[:n], A, D, model.R, model.FR_MONT_R))
+            assert aff(oracle, ctx.msm(srs_plain, s_all[:n])) == want, ("plain", n)
+            assert aff(oracle, ctx.msm(srs_pre, s_all[:n])) == want, ("pre", n)
+    finally:
+        ctx.srs_free(srs_plain)
+        ctx.srs_free(srs_pre)
