@@ -18,6 +18,8 @@ struct Field;
 #if defined(PB_FIELD_NOINLINE_MUL) && defined(__CUDACC__)
 template <class P>
 __device__ __noinline__ Field<P> field_mul_noinline(Field<P> a, Field<P> b);  // operands travel in registers
+template <class P>
+__device__ __noinline__ Field<P> field_sqr_noinline(Field<P> a);
 #endif
 
 template <class P>
@@ -179,7 +181,69 @@ struct Field {
         return mul_inline(a, b);
 #endif
     }
-    PB_HD Field sqr() const { return *this * *this; }
+    // ---- squaring (fields with ≥ 3 spare top bits: Fp) ------------------------------------------------
+    // a² = Σ_i a_i·(a_i + 2·Σ_{j>i} a_j 2^(32(j−i)))·2^(64 i): row i of the word-serial loop only needs the products
+    // with j ≥ i, taken against the pre-doubled operand (78 instead of 144 products; the 144 of the interleaved
+    // reduction stay).  Doubling raises the bound on the running value from 2p to 3p and on the window from
+    // 2^33·p to 3·2^32·p, which still fits 32(N+1) bits because p < 2^(32N−3); two conditional subtractions finish.
+    // x_j for row i: 0 (j < i) | a_i (j = i) | a_(i+1) << 1 (j = i+1) | d_j = (a_j << 1 | a_(j−1) >> 31) (j > i+1).
+    PB_HD static uint64_t sqr_term(const uint32_t *a, const uint32_t *d, int i, int j) {
+        if (j < i) return 0;
+        if (j == i) return cc::mul_wide(a[i], a[i]);
+        if (j == i + 1) return cc::mul_wide(a[j] << 1, a[i]);
+        return cc::mul_wide(d[j], a[i]);
+    }
+    PB_HD static void round_sqr(uint64_t *S, uint64_t *D, const uint32_t *a, const uint32_t *d, int i) {
+        uint32_t d0 = cc::add_cc(cc::lo32(D[0]), cc::hi32(S[0]));
+#pragma unroll
+        for (int k = 0; k < H - 1; k++) S[k] = cc::addc_cc64(S[k + 1], sqr_term(a, d, i, 2 * k + 1));
+        S[H - 1] = cc::addc64(sqr_term(a, d, i, N - 1), 0);
+        D[0] = cc::add_cc64(cc::pack64(d0, cc::hi32(D[0])), sqr_term(a, d, i, 0));
+#pragma unroll
+        for (int k = 1; k < H; k++) D[k] = cc::addc_cc64(D[k], sqr_term(a, d, i, 2 * k));
+        S[H - 1] = cc::pack64(cc::lo32(S[H - 1]), cc::addc(cc::hi32(S[H - 1]), 0));
+        redc_step(D, S);
+    }
+    PB_HD static Field sqr_inline(const Field &x) {
+        const uint32_t *a = x.l;
+        uint32_t d[N];
+        d[0] = a[0] << 1;
+#pragma unroll
+        for (int j = 1; j < N; j++) d[j] = (a[j] << 1) | (a[j - 1] >> 31);  // a[N−1] >> 31 = 0: spare bits
+        uint64_t A[H], B[H];
+#pragma unroll
+        for (int k = 0; k < H; k++) {
+            A[k] = sqr_term(a, d, 0, 2 * k);
+            B[k] = sqr_term(a, d, 0, 2 * k + 1);
+        }
+        redc_step(A, B);
+#pragma unroll
+        for (int i = 1; i < N - 1; i += 2) {
+            round_sqr(A, B, a, d, i);
+            round_sqr(B, A, a, d, i + 1);
+        }
+        round_sqr(A, B, a, d, N - 1);
+        Field r;
+        r.l[0] = cc::add_cc(cc::lo32(A[0]), cc::hi32(B[0]));
+#pragma unroll
+        for (int k = 1; k < N - 1; k++) {
+            uint32_t u = (k & 1) ? cc::hi32(A[k >> 1]) : cc::lo32(A[k >> 1]);
+            uint32_t v = (k & 1) ? cc::lo32(B[(k + 1) >> 1]) : cc::hi32(B[k >> 1]);
+            r.l[k] = cc::addc_cc(u, v);
+        }
+        r.l[N - 1] = cc::addc(cc::hi32(A[H - 1]), 0);
+        return reduce_once(reduce_once(r));  // value < 3p
+    }
+    PB_HD Field sqr() const {
+        if (P::SPARE_BITS >= 3) {
+#if defined(PB_FIELD_NOINLINE_MUL) && defined(__CUDA_ARCH__)
+            return field_sqr_noinline(*this);
+#else
+            return sqr_inline(*this);
+#endif
+        }
+        return *this * *this;
+    }
 
     // Montgomery form → canonical integer (multiply by 1): N elimination rounds, no products with b.
     PB_HD Field from_mont() const {
@@ -217,6 +281,10 @@ template <class P>
 __device__ __noinline__ Field<P> field_mul_noinline(Field<P> a, Field<P> b) {
     return Field<P>::mul_inline(a, b);
 }
+template <class P>
+__device__ __noinline__ Field<P> field_sqr_noinline(Field<P> a) {
+    return Field<P>::sqr_inline(a);
+}
 #endif
 
 // ---------------------------------------------------------------------------------------------------
@@ -225,6 +293,7 @@ struct FrParams {
     static constexpr int N = 8;
     static constexpr uint32_t INV32 = 0xffffffffu;
     static constexpr bool LOW_LIMBS_1_FFFFFFFF = true;
+    static constexpr int SPARE_BITS = 1;  // 255-bit modulus in 256
     PB_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t v[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
                                    0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
@@ -246,6 +315,7 @@ struct FpParams {
     static constexpr int N = 12;
     static constexpr uint32_t INV32 = 0xfffcfffdu;
     static constexpr bool LOW_LIMBS_1_FFFFFFFF = false;
+    static constexpr int SPARE_BITS = 3;  // 381-bit modulus in 384
     PB_HD static constexpr uint32_t mod(int i) {
         constexpr uint32_t v[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
                                     0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};

@@ -17,6 +17,7 @@ template <class F> static void binop(int op, const uint32_t *a, const uint32_t *
             case 4: z = x.to_mont(); break;
             case 5: z = x.inv(); break;
             case 6: z = x.neg(); break;
+            case 7: z = x.sqr(); break;
             default: z = F::one();
         }
         memcpy(o + F::N * i, z.l, 4 * F::N);

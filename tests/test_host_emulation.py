@@ -58,6 +58,7 @@ def test_fr_matches_oracle(emu, oracle):
     assert (_run(emu, "emu_fr", 3, a, b) == oracle.fr_from_mont(a)).all()
     assert (_run(emu, "emu_fr", 4, a, b) == oracle.fr_to_mont(a)).all()
     assert (_run(emu, "emu_fr", 5, a[:64], b[:64]) == oracle.fr_inv(a[:64])).all()
+    assert (_run(emu, "emu_fr", 7, a, b) == oracle.fr_mul(a, a)).all()   # Fr has 1 spare bit: sqr falls back to mul
 
 
 def test_fp_matches_oracle(emu, oracle):
@@ -71,6 +72,11 @@ def test_fp_matches_oracle(emu, oracle):
     assert (_run(emu, "emu_fp", 3, a, b) == oracle.fp_from_mont(a)).all()
     assert (_run(emu, "emu_fp", 4, a, b) == oracle.fp_to_mont(a)).all()
     assert (_run(emu, "emu_fp", 5, a[:32], b[:32]) == oracle.fp_inv(a[:32])).all()
+    # dedicated squaring (triangular products on the pre-doubled operand) incl. the extreme values p−1, p−2, 2^380
+    assert (_run(emu, "emu_fp", 7, a, b) == oracle.fp_mul(a, a)).all()
+    top = oracle.ints_to_limbs([model.P - 1 - k for k in range(64)] + [(1 << 381) - 1 - 3 * k for k in range(64)
+                                                                        if (1 << 381) - 1 - 3 * k < model.P], 6)
+    assert (_run(emu, "emu_fp", 7, top, top) == oracle.fp_mul(top, top)).all()
 
 
 def _g1(lib, op, P, Q, k=0):
