@@ -317,7 +317,10 @@ def run_ours(args, rank, world, local_rank):
         extra["roofline"] = {
             "bound": "imad", "kernel": "msm_accumulate_kernel",
             "achieved": alg_imad / (acc * 1e-3) / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE.U32 lane-op/s",
-            "frac": alg_imad / (acc * 1e-3) / imad_peak, "traffic": None,
+            "frac": alg_imad / (acc * 1e-3) / imad_peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 2^26, ncu --set full (profiles/ncu_full_r01_summary.txt):
+            # 161.2 + 5.8 GB against ~84 GB of entries + gathered bases — irrelevant next to the integer work
+            "traffic": 167.0e9 if L == 26 else None,
             "peak_source": "pb200_imad_peak: IMAD.WIDE.U32.X carry-chain microbenchmark, this run (MEASURED_PEAKS.json has no "
                            "integer peak); see profiles/imad_explore_r01.txt",
             "model": "N*ceil(256/(log2N-4))*10 Fp mul * 300 IMAD.WIDE (SURVEY.md §8d: 600 lo+hi lane-ops at 64/clk/SM "
@@ -472,7 +475,9 @@ def bench_ntt(ctx, stream, args, imad_peak):
         "e2e": {"value": n / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "ms": e2e_ms, "h2d_bytes_per_step": n * 32,
                 "d2h_bytes_per_step": n * 32},
         "roofline": {"bound": "hbm", "achieved": alg_bytes_survey / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                     "frac": alg_bytes_survey / (ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                     "frac": alg_bytes_survey / (ms * 1e-3) / 1e9 / hbm,
+                     # per launch of ntt_pass_kernel at 2^24 (one of three passes): 0.54 GB read + 0.64 GB written (ncu)
+                     "traffic": 1.175e9 if L == 24 else None, "traffic_unit": "bytes per pass launch (algorithmic: 64 B * n)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
                      "model": "64 B * n * ceil(log2 n / 12) (SURVEY.md §8d); this build moves 64 B * n * %d" % passes,
                      "moved_bytes_frac": alg_bytes / (ms * 1e-3) / 1e9 / hbm},
