@@ -87,6 +87,17 @@ PB200_API int pb200_ntt_batch_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t l
  * ω_n^{±col·k} of the 2^log_n transform (forward: after the columns; inverse: before them, plus the 2^-log_n1 scale). */
 PB200_API int pb200_ntt_columns_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, uint32_t log_n1, uint32_t log_cols,
                                     uint32_t col_offset, int inverse);
+/* Fused compute + exchange (forward direction): the same column step, but every output is stored straight into the
+ * row-layout buffer of the rank that owns its row — peer memory over NVLink / NVSwitch — so the all-to-all and the
+ * block transpose ARE the kernel's store and overlap its arithmetic tile by tile.  peer_row_bufs[h] is rank h's
+ * receive buffer of (2^log_n1 / world) rows × (2^log_n / 2^log_n1) scalars (its own for h = this rank); remote ones
+ * come from pb200_ipc_open.  The caller barriers all ranks before reading its buffer. */
+PB200_API int pb200_ntt_columns_scatter_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, uint32_t log_n1, uint32_t log_cols,
+                                            uint32_t col_offset, uint32_t world, void *const *peer_row_bufs);
+/* CUDA IPC plumbing for one-process-per-GPU hosts: export a pb200_malloc'ed buffer / map a peer's buffer. */
+PB200_API int pb200_ipc_export(pb200_ctx *ctx, void *dev_ptr, unsigned char handle_out[64]);
+PB200_API int pb200_ipc_open(pb200_ctx *ctx, const unsigned char handle[64], void **dev_ptr_out);
+PB200_API int pb200_ipc_close(pb200_ctx *ctx, void *dev_ptr);
 /* dst[(r·blocks + b)·cols + c] = src[(b·rows + r)·cols + c] on 32-byte scalars: regroups what an all-to-all delivered. */
 PB200_API int pb200_block_transpose_dev(pb200_ctx *ctx, uint64_t *dst_dev, const uint64_t *src_dev, uint32_t blocks,
                                         uint32_t rows, uint32_t cols);

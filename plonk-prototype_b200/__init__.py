@@ -3,4 +3,4 @@ surface that Manta-Network/Plonk-Prototype's circuits prove through.  See DESIGN
 from ._native import Context, Pb200Error, LIB_PATH, EXPORTS  # noqa: F401
 from .domain import EvaluationDomain, InvalidEvalDomainSize, default_context  # noqa: F401
 from .msm import msm_variable_base, CommitKey, g1_to_bytes  # noqa: F401
-from .dist_ntt import DistributedDomain, ShardSpec, GpuBackend  # noqa: F401
+from .dist_ntt import DistributedDomain, ShardSpec, GpuBackend, PeerBuffers  # noqa: F401

@@ -15,7 +15,8 @@ _lib = None
 EXPORTS = [
     "pb200_init", "pb200_destroy", "pb200_last_error", "pb200_stream", "pb200_sync",
     "pb200_malloc", "pb200_free", "pb200_h2d", "pb200_d2h",
-    "pb200_domain_log_size", "pb200_ntt", "pb200_ntt_dev", "pb200_ntt_batch_dev", "pb200_ntt_columns_dev", "pb200_block_transpose_dev",
+    "pb200_domain_log_size", "pb200_ntt", "pb200_ntt_dev", "pb200_ntt_batch_dev", "pb200_ntt_columns_dev", "pb200_ntt_columns_scatter_dev",
+    "pb200_ipc_export", "pb200_ipc_open", "pb200_ipc_close", "pb200_block_transpose_dev",
     "pb200_srs_upload", "pb200_srs_wrap_dev", "pb200_srs_precompute", "pb200_srs_free", "pb200_srs_len",
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_g1_sum", "pb200_msm_window_bits",
     "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_launch_count",
@@ -52,6 +53,11 @@ def lib():
         L.pb200_ntt_dev.argtypes = [vp, u64p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
         L.pb200_ntt_batch_dev.argtypes = [vp, u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int, ctypes.c_int]
         L.pb200_ntt_columns_dev.argtypes = [vp, u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_int]
+        L.pb200_ntt_columns_scatter_dev.argtypes = [vp, u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                                    ctypes.c_uint32, ctypes.POINTER(vp)]
+        L.pb200_ipc_export.argtypes = [vp, vp, ctypes.c_char_p]
+        L.pb200_ipc_open.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
+        L.pb200_ipc_close.argtypes = [vp, vp]
         L.pb200_block_transpose_dev.argtypes = [vp, u64p, u64p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
         L.pb200_srs_upload.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.POINTER(vp)]
         L.pb200_srs_wrap_dev.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.POINTER(vp)]
@@ -147,6 +153,24 @@ class Context:
 
     def ntt_columns_dev(self, dev, log_n, log_n1, log_cols, col_offset, inverse=False):
         self._check(lib().pb200_ntt_columns_dev(self._h, ctypes.c_void_p(dev), log_n, log_n1, log_cols, col_offset, int(inverse)))
+
+    def ntt_columns_scatter_dev(self, dev, log_n, log_n1, log_cols, col_offset, peer_row_bufs):
+        arr = (ctypes.c_void_p * len(peer_row_bufs))(*[int(p) for p in peer_row_bufs])
+        self._check(lib().pb200_ntt_columns_scatter_dev(self._h, ctypes.c_void_p(dev), log_n, log_n1, log_cols, col_offset,
+                                                        len(peer_row_bufs), arr))
+
+    def ipc_export(self, dev):
+        buf = ctypes.create_string_buffer(64)
+        self._check(lib().pb200_ipc_export(self._h, ctypes.c_void_p(dev), buf))
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = ctypes.c_void_p()
+        self._check(lib().pb200_ipc_open(self._h, handle, ctypes.byref(p)))
+        return p.value
+
+    def ipc_close(self, dev):
+        self._check(lib().pb200_ipc_close(self._h, ctypes.c_void_p(dev)))
 
     def block_transpose_dev(self, dst, src, blocks, rows, cols):
         self._check(lib().pb200_block_transpose_dev(self._h, ctypes.c_void_p(dst), ctypes.c_void_p(src), blocks, rows, cols))

@@ -41,6 +41,11 @@ struct NttPass {
     const Fr *l_lo, *l_hi, *s_lo, *s_hi;
     const Fr *s_const;
     const Fr *l_full, *s_full;  // single-lookup tables (one multiply instead of two)
+    // type 0 only — fused exchange of the sharded four-step: when peer_log_rl != 0xffffffff the store goes straight
+    // into the destination rank's row-layout buffer (peer memory over NVLink, CUDA IPC): row k belongs to rank
+    // k >> peer_log_rl and lands at [(k mod rl)·m + col_offset + col], i.e. all-to-all and transpose are the store.
+    uint32_t peer_log_rl, peer_log_m;
+    Fr *peer[8];
 };
 
 __device__ __forceinline__ Fr g_load(const Fr *p) {
@@ -212,6 +217,11 @@ __global__ void __launch_bounds__(256, 2) ntt_pass_kernel(const Fr *__restrict__
             addr = in_base + ((uint64_t)k << p.ncol_log) + c;
             if (p.store_mode == 2) v = v * pow2level(p.s_lo, p.s_hi, p.s_B, ((p.col_offset + col0 + c) * k) << p.mult_log);
             else if (p.store_mode == 4) v = v * g_load(p.s_full + (((uint64_t)k << p.ncol_log) + col0 + c));
+            if (p.peer_log_rl != 0xffffffffu) {
+                Fr *dst = p.peer[k >> p.peer_log_rl];
+                g_store(dst + (((uint64_t)(k & ((1u << p.peer_log_rl) - 1)) << p.peer_log_m) + p.col_offset + col0 + c), v);
+                continue;
+            }
         } else {
             addr = (uint64_t)(rowrev0 + c) + ((uint64_t)k << p.nrows_log);
             if (p.store_mode == 3) v = v * pow2level(p.s_lo, p.s_hi, p.s_B, (uint32_t)addr);
@@ -382,6 +392,7 @@ static int ntt_build_plan(pb200_ctx *ctx, uint32_t L, int inverse, int coset, Nt
     for (int i = 0; i < P; i++) {
         NttPass &p = pl->pass[i];
         memset(&p, 0, sizeof(p));
+        p.peer_log_rl = 0xffffffffu;
         p.S = S[i];
         Fr *tw = nullptr;
         PB_TRY(fill_powers(ctx, pl, &tw, 1u << (S[i] - 1), c_w, 1ull << (L - S[i]), c_one));
@@ -544,8 +555,8 @@ extern "C" int pb200_ntt(pb200_ctx *ctx, uint64_t *data_host, uint32_t log_n, in
 //   forward: length-n1 NTT down every column, then × ω_n^{(col_offset + col)·k1}          (before the all-to-all)
 //   inverse: × ω_n^{−(col_offset + col)·k1}, then length-n1 iNTT down every column, × n1⁻¹  (after the all-to-all back)
 // One pass, in place; log_n1 ≤ 11.
-extern "C" int pb200_ntt_columns_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, uint32_t log_n1, uint32_t log_cols,
-                                     uint32_t col_offset, int inverse) {
+static int ntt_columns_impl(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, uint32_t log_n1, uint32_t log_cols, uint32_t col_offset,
+                            int inverse, uint32_t world, void *const *peer_rows) {
     if (!ctx) return PB200_ERR_ARG;
     PB_ARG(ctx, data_dev != nullptr);
     PB_ARG(ctx, log_n < kTwoAdicity && log_n1 >= 3 && log_n1 <= kTileLogMax && log_n1 + log_cols <= log_n);
@@ -583,6 +594,7 @@ extern "C" int pb200_ntt_columns_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_
         PB_TRY(fill_powers(ctx, pl, &tw, 1u << (log_n1 - 1), c_w, 1ull << (log_n - log_n1), c_one));
         NttPass &p = pl->pass[0];
         memset(&p, 0, sizeof(p));
+        p.peer_log_rl = 0xffffffffu;
         p.S = log_n1;
         p.type = 0;
         p.tw = tw;
@@ -594,6 +606,13 @@ extern "C" int pb200_ntt_columns_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_
     p.ncol_log = log_cols;
     p.col_offset = col_offset;
     p.mult_log = 0;  // the twiddle is ω_n^{j'·k1} with j' the global column index in [0, n / n1)
+    if (peer_rows) {
+        uint32_t log_g = 0;
+        while ((1u << log_g) < world) log_g++;
+        p.peer_log_rl = log_n1 - log_g;
+        p.peer_log_m = log_n - log_n1;
+        for (uint32_t h = 0; h < world; h++) p.peer[h] = (Fr *)peer_rows[h];
+    }
     const uint32_t tile_log = std::max(log_n1, std::min(10u, log_n1 + log_cols));
     p.logC = std::min(tile_log - log_n1, log_cols);
     const uint32_t T = 1u << (p.S + p.logC);
@@ -601,6 +620,41 @@ extern "C" int pb200_ntt_columns_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_
     const uint32_t blocks = 1u << (log_cols - p.logC);
     ntt_pass_kernel<<<blocks, T >> 3, smem, ctx->stream>>>((const Fr *)data_dev, (Fr *)data_dev, p);
     PB_LAUNCHED(ctx);
+    return 0;
+}
+extern "C" int pb200_ntt_columns_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, uint32_t log_n1, uint32_t log_cols,
+                                     uint32_t col_offset, int inverse) {
+    return ntt_columns_impl(ctx, data_dev, log_n, log_n1, log_cols, col_offset, inverse, 0, nullptr);
+}
+extern "C" int pb200_ntt_columns_scatter_dev(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, uint32_t log_n1, uint32_t log_cols,
+                                             uint32_t col_offset, uint32_t world, void *const *peer_row_bufs) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, peer_row_bufs != nullptr && world >= 1 && world <= 8 && (world & (world - 1)) == 0 && (1u << log_n1) >= world);
+    for (uint32_t h = 0; h < world; h++) PB_ARG(ctx, peer_row_bufs[h] != nullptr && peer_row_bufs[h] != (void *)data_dev);
+    return ntt_columns_impl(ctx, data_dev, log_n, log_n1, log_cols, col_offset, 0, world, peer_row_bufs);
+}
+// CUDA IPC plumbing so that one-process-per-GPU hosts can hand each other their receive buffers.
+extern "C" int pb200_ipc_export(pb200_ctx *ctx, void *dev_ptr, unsigned char handle_out[64]) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, dev_ptr != nullptr && handle_out != nullptr);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    PB_CUDA(ctx, cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+extern "C" int pb200_ipc_open(pb200_ctx *ctx, const unsigned char handle[64], void **dev_ptr_out) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, handle != nullptr && dev_ptr_out != nullptr);
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    PB_CUDA(ctx, cudaIpcOpenMemHandle(dev_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+extern "C" int pb200_ipc_close(pb200_ctx *ctx, void *dev_ptr) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_CUDA(ctx, cudaIpcCloseMemHandle(dev_ptr));
     return 0;
 }
 extern "C" int pb200_block_transpose_dev(pb200_ctx *ctx, uint64_t *dst_dev, const uint64_t *src_dev, uint32_t blocks, uint32_t rows,

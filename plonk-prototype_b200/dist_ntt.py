@@ -79,6 +79,16 @@ class DistributedDomain:
         be.rows(buf, s.rl, s.log_n - s.log_n1, inverse=False)
         return buf
 
+    def fft_fused(self, buf, peers):
+        """Forward transform with the exchange fused into the column kernel: every rank's column pass stores its
+        outputs directly into the owners' row-layout buffers (`peers` = PeerBuffers: NVLink peer memory), then one
+        barrier, then the local rows.  The result (row layout) is in peers.mine; `buf` is consumed."""
+        s, be = self.spec, self.backend
+        be.columns_scatter(buf, s.log_n, s.log_n1, s.cl, self.rank * s.cl, peers)
+        be.barrier()                                           # every rank has finished writing into every buffer
+        be.rows(peers.mine, s.rl, s.log_n - s.log_n1, inverse=False)
+        return peers.mine
+
     def ifft(self, buf, tmp):
         s, be = self.spec, self.backend
         be.rows(buf, s.rl, s.log_n - s.log_n1, inverse=True)   # includes m⁻¹
@@ -110,3 +120,51 @@ class GpuBackend:
     def all_to_all(self, out, inp, world):
         with self.torch.cuda.stream(self.stream):               # ordered after the kernels on the library's stream
             self.dist.all_to_all_single(out, inp)
+
+    # ---- fused exchange over peer memory -----------------------------------------------------------------
+    def columns_scatter(self, buf, log_n, log_n1, cols, col_offset, peers):
+        self.ctx.ntt_columns_scatter_dev(_ptr_of(buf), log_n, log_n1, cols.bit_length() - 1, col_offset, peers.ptrs)
+
+    def barrier(self):
+        self.ctx.sync()
+        if self.dist is not None:
+            self.dist.barrier()
+
+
+class _RawBuffer:
+    """A pb200_malloc'ed device buffer with the data_ptr() interface the backend expects (IPC needs cudaMalloc memory)."""
+
+    def __init__(self, ctx, nbytes):
+        self.ctx, self.ptr, self.nbytes = ctx, ctx.malloc(nbytes), nbytes
+
+    def data_ptr(self):
+        return self.ptr
+
+
+def _ptr_of(buf):
+    return buf.data_ptr()
+
+
+class PeerBuffers:
+    """One row-layout receive buffer per rank, mapped into every other rank with CUDA IPC (NVLink peer memory)."""
+
+    def __init__(self, ctx, dist, rank, world, n_local_scalars):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.mine = _RawBuffer(ctx, n_local_scalars * 32)
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.ipc_export(self.mine.ptr))
+        self._opened = []
+        self.ptrs = []
+        for h in range(world):
+            if h == rank:
+                self.ptrs.append(self.mine.ptr)
+            else:
+                p = ctx.ipc_open(handles[h])
+                self._opened.append(p)
+                self.ptrs.append(p)
+
+    def close(self):
+        for p in self._opened:
+            self.ctx.ipc_close(p)
+        self._opened = []
+        self.ctx.free(self.mine.ptr)

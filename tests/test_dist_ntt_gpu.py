@@ -67,3 +67,25 @@ def test_emulated_ranks_match_single_gpu_and_oracle(ctx, oracle, world, log_n, l
         assert (got == oracle.ntt(x, 0, 0, threads=8)).all()
     _, back = em.run(log_n, [spec.scatter(got, g, "row") for g in range(world)], True, log_n1)
     assert (spec.gather(back, "column") == x).all()          # ifft(fft(x)) = x through the sharded path
+
+
+@pytest.mark.parametrize("world,log_n,log_n1", [(2, 14, 8), (4, 16, 8), (8, 18, 9)])
+def test_fused_column_scatter_writes_row_layout(ctx, oracle, world, log_n, log_n1):
+    """pb200_ntt_columns_scatter_dev: the column pass stores straight into every owner's row-layout buffer (here the
+    'peers' are other buffers on the same GPU); after the local rows the result equals the single-GPU transform."""
+    import plonk_prototype_b200 as pb
+    x = oracle.fr_to_mont(oracle.random_fr(0xF05E + log_n, 1 << log_n))
+    spec = pb.ShardSpec(log_n, world, log_n1)
+    cols = [torch.from_numpy(spec.scatter(x, g, "column").view(np.int64).reshape(-1).copy()).cuda() for g in range(world)]
+    rows = [torch.zeros(spec.local * 4, dtype=torch.int64, device="cuda") for _ in range(world)]
+    ptrs = [r.data_ptr() for r in rows]
+    for g in range(world):
+        ctx.ntt_columns_scatter_dev(cols[g].data_ptr(), log_n, log_n1, spec.cl.bit_length() - 1, g * spec.cl, ptrs)
+    ctx.sync()
+    for g in range(world):
+        ctx.ntt_batch_dev(rows[g].data_ptr(), log_n - log_n1, spec.rl, False, False)
+    ctx.sync()
+    got = spec.gather([r.cpu().numpy().view(np.uint64).reshape(-1, 4) for r in rows], "row")
+    want = x.copy()
+    ctx.ntt(want, log_n, False, False)
+    assert (got == want).all()
