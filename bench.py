@@ -410,12 +410,39 @@ def bench_ntt_sharded(ctx, dist, rank, world, args):
         dom.fft(buf, tmp)
     e1.record(be.stream)
     ctx.sync(); torch.cuda.synchronize(); dist.barrier()
-    t = torch.tensor([e0.elapsed_time(e1) / reps, 0.0 if ok else 1.0], device="cuda", dtype=torch.float64)
+    nccl_ms = e0.elapsed_time(e1) / reps
+    # fused variant: the column kernel stores straight into the peers' row buffers (CUDA IPC over NVLink); wall clock
+    # per transform including the cross-rank barrier, median of 10, input restored between repetitions
+    peers = pb.PeerBuffers(ctx, dist, rank, world, spec.local)
+    col = torch.from_numpy(shard.view(np.int64).reshape(-1).copy()).cuda()
+    work = torch.empty_like(col)
+    ts = []
+    for i in range(13):
+        work.copy_(col); torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        dom.fft_fused(work, peers)
+        ctx.sync()
+        if i >= 3:
+            ts.append((time.perf_counter() - t0) * 1e3)
+    fused_ms = sorted(ts)[len(ts) // 2]
+    # the fused result must equal the NCCL result (itself checked against the single-GPU transform in tests)
+    buf.copy_(col)
+    dom.fft(buf, tmp)
+    ctx.sync(); torch.cuda.synchronize()
+    fused_out = np.empty((spec.local, 4), np.uint64)
+    ctx.d2h(fused_out, peers.mine.ptr)
+    same = bool((fused_out == buf.cpu().numpy().view(np.uint64).reshape(-1, 4)).all())
+    peers.close()
+    t = torch.tensor([nccl_ms, fused_ms, 0.0 if (ok and same) else 1.0], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, bad = t.tolist()
+    nccl_ms, fused_ms, bad = t.tolist()
+    ms = min(nccl_ms, fused_ms)
     return {"metric": "sharded four-step NTT, 2^%d points over %d GPUs (forward)" % (L, world), "ms": ms,
             "value": (1 << L) / (ms * 1e-3) / 1e6, "unit": "Melem/s", "scaling": "strong", "n1": spec.n1,
-            "exchange_bytes_per_gpu": spec.local * 32 * (world - 1) // world, "roundtrip_verified": bad == 0.0}
+            "fused_peer_store_ms": fused_ms, "nccl_all_to_all_ms": nccl_ms,
+            "exchange_bytes_per_gpu": spec.local * 32 * (world - 1) // world,
+            "verified": bad == 0.0, "note": "fused: column kernel writes the owners' row buffers over NVLink peer memory, "
+            "wall clock incl. the cross-rank barrier; nccl: column kernel + all_to_all_single + transpose kernel, CUDA events"}
 
 
 def bench_ntt(ctx, stream, args, imad_peak):

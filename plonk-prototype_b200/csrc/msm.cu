@@ -15,6 +15,7 @@
 //   5. reduce   Σ_b b·B_b per window as chunked running sums, then a per-window tree sum
 //   6. combine  Horner over the windows (c doublings each), normalise to affine
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "msm_common.cuh"
@@ -53,8 +54,12 @@ __global__ void __launch_bounds__(256) msm_count_kernel(const uint64_t *scalars,
     }
 }
 // `shift` = 0: entries go straight to their bucket's slot range (cursor = per-bucket offsets).
-// `shift` > 0: first level of the two-level scatter — the cursor array is per *coarse bin* (2^shift buckets) and
-// entries are only grouped by bin; msm_fine_scatter_kernel finishes the job.
+// `shift` > 0: first level of the two-level scatter used once the entry list outgrows L2 — the cursor array is per
+// *coarse bin* (2^shift buckets, ≈ 32 Ki entries) and entries are only grouped by bin.  All CTAs share one write
+// frontier per bin, so the open lines (bins × 128 B) stay in L2 and reach DRAM complete: ncu shows 6.65 GB written
+// for 6.44 GB of entries at 2^26, against one 32-byte sector per 8-byte entry for the single-level scatter.
+// (Reserving per-CTA runs from shared-memory histograms was tried: fewer global atomics, but the open set becomes
+// in-flight-entries × 8 B ≈ 465 MB ≫ L2 and DRAM traffic triples — 74 ms instead of 42 ms — so it was dropped.)
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint64_t *scalars, MsmCfg cfg, uint32_t *cursor, uint2 *entries,
                                                           uint32_t shift) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cfg.n; i += (size_t)gridDim.x * blockDim.x) {
@@ -72,8 +77,8 @@ __global__ void msm_coarse_init_kernel(const uint32_t *offsets, uint32_t *coarse
     if (b < n_coarse) coarse[b] = offsets[b << shift];
 }
 // Second level: walk the bin-grouped list in order; each entry moves to its bucket's slot.  CTAs that run at the
-// same time cover a few neighbouring bins, so the scattered 8-byte writes stay inside an L2-resident window and
-// reach DRAM as full lines (the single-level scatter wrote one 32-byte sector per entry all over a 6 GB array).
+// same time cover a few neighbouring bins, so the scattered 8-byte writes stay inside an L2-resident window.
+// Both levels are bound by global atomics with return (~45-50 G/s on B200).
 __global__ void __launch_bounds__(256) msm_fine_scatter_kernel(const uint2 *__restrict__ grouped, const uint32_t *__restrict__ n_entries_ptr,
                                                                uint32_t *cursor, uint2 *entries) {
     const uint32_t M = *n_entries_ptr;
@@ -269,7 +274,9 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     const size_t o_entries = carve((size_t)m0 * 8);
     // two-level scatter once the entry list outgrows L2: coarse bins of ~32 Ki entries, never crossing a window
     uint32_t coarse_shift = 0;
-    if (m0 * 8 > ((size_t)1 << 30)) {
+    size_t two_level_min = (size_t)1 << 30;
+    if (const char *v = getenv("PB200_MSM_TWO_LEVEL_MIN_BYTES")) two_level_min = (size_t)atoll(v);  // tests force the path at small sizes
+    if (m0 * 8 > two_level_min) {
         const double per_bucket = std::max(1.0, (double)m0 / (double)TB);
         while (coarse_shift < cfg.nb_log && per_bucket * (double)(2u << coarse_shift) <= 32768.0) coarse_shift++;
     }

@@ -225,3 +225,28 @@ def test_many_sizes_closed_form(ctx, oracle):
     finally:
         ctx.srs_free(srs_plain)
         ctx.srs_free(srs_pre)
+
+
+def test_two_level_scatter_path(ctx, oracle, monkeypatch):
+    """The two-level scatter (shared-memory histograms + CTA-per-bin fine pass) normally only runs above 1 GB of
+    entries; force it at small sizes, including skewed digit distributions and the pre-doubled SRS mode."""
+    monkeypatch.setenv("PB200_MSM_TWO_LEVEL_MIN_BYTES", "0")
+    n = 1 << 15
+    pts = oracle.synthetic_bases(n)
+    srs = ctx.srs_upload(pts)
+    srs_pre = ctx.srs_upload(pts)
+    ctx.srs_precompute(srs_pre)
+    rnd = model.random_fr(0x2C, n)
+    sets = {"random": rnd, "all_one": [1] * n, "eight_bit": [v & 0xFF for v in rnd], "all_r_minus_1": [model.R - 1] * n,
+            "one_heavy_bucket": [0x1234 if i % 3 else v for i, v in enumerate(rnd)]}
+    try:
+        for name, vals in sets.items():
+            s = oracle.fr_to_mont(oracle.ints_to_limbs(vals, 4))
+            want = model.g1_mul(model.G1_GEN, closed_form_msm_scalar(s, A, D, model.R, model.FR_MONT_R))
+            for m in (n, 40000 // 3, 1000):
+                w = want if m == n else model.g1_mul(model.G1_GEN, closed_form_msm_scalar(s[:m], A, D, model.R, model.FR_MONT_R))
+                assert aff(oracle, ctx.msm(srs, s[:m])) == w, (name, m, "plain")
+                assert aff(oracle, ctx.msm(srs_pre, s[:m])) == w, (name, m, "pre")
+    finally:
+        ctx.srs_free(srs)
+        ctx.srs_free(srs_pre)
