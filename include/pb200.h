@@ -127,6 +127,22 @@ PB200_API int pb200_g1_sum(pb200_ctx *ctx, const uint64_t *points_xyz_mont_host,
 /* Pippenger window width used for n points (exposed for the benches' work model). */
 PB200_API uint32_t pb200_msm_window_bits(size_t n);
 
+/* ---- KZG10 layer above the MSM: dusk_plonk::commitment_scheme::kzg10 ---------------- */
+/* PublicParameters::setup: powers_of_g[i] = τ^i·G for i < n_points, generated on the device and resident (τ given
+ * in Montgomery form, non-zero; the G2 side of the parameters belongs to the host verifier). */
+PB200_API int pb200_srs_generate(pb200_ctx *ctx, const uint64_t tau_mont[4], size_t n_points, pb200_srs **out);
+/* Device address of an SRS's packed affine points (n × 96 B), e.g. to serialise the CommitKey. */
+PB200_API const uint64_t *pb200_srs_dev_ptr(const pb200_srs *srs);
+/* CommitKey::compute_single_witness: p(z) and q(X) = (p(X) − p(z)) / (X − z) for a device-resident polynomial of
+ * n coefficients (Ruffini's rule as scale → Fr suffix scan → scale).  quotient_dev receives n scalars (the top one
+ * is zero).  Blocks; p(z) is returned on the host. */
+PB200_API int pb200_kzg_witness_dev(pb200_ctx *ctx, const uint64_t *poly_dev, size_t n, const uint64_t z_mont[4],
+                                    uint64_t *quotient_dev, uint64_t eval_mont_out[4]);
+/* One Horner step over whole polynomials, acc[j] ← acc[j]·c + poly[j] (poly zero-padded to n_acc): the
+ * random-linear-combination Σ vⁱ·pᵢ of CommitKey::compute_aggregate_witness. */
+PB200_API int pb200_fr_horner_step_dev(pb200_ctx *ctx, uint64_t *acc_dev, size_t n_acc, const uint64_t *poly_dev, size_t n_poly,
+                                       const uint64_t c_mont[4]);
+
 /* ---- synthetic workloads & measurement helpers (bench.py / tests) -------------- */
 /* bases[i] = (a + i·d)·G, packed affine Montgomery, written to a device buffer of n × 96 B. */
 PB200_API int pb200_synthetic_bases_dev(pb200_ctx *ctx, uint64_t *xy_mont_dev, size_t n, uint64_t a, uint64_t d);

@@ -19,6 +19,7 @@ EXPORTS = [
     "pb200_ipc_export", "pb200_ipc_open", "pb200_ipc_close", "pb200_block_transpose_dev",
     "pb200_srs_upload", "pb200_srs_wrap_dev", "pb200_srs_precompute", "pb200_srs_free", "pb200_srs_len",
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_g1_sum", "pb200_msm_window_bits",
+    "pb200_srs_generate", "pb200_srs_dev_ptr", "pb200_kzg_witness_dev", "pb200_fr_horner_step_dev",
     "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_launch_count",
     "pb200_imad_peak",
 ]
@@ -71,6 +72,11 @@ def lib():
         L.pb200_g1_sum.argtypes = [vp, u64p, ctypes.c_size_t, u64p]
         L.pb200_msm_window_bits.argtypes = [ctypes.c_size_t]
         L.pb200_msm_window_bits.restype = ctypes.c_uint32
+        L.pb200_srs_generate.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.POINTER(vp)]
+        L.pb200_srs_dev_ptr.argtypes = [vp]
+        L.pb200_srs_dev_ptr.restype = vp
+        L.pb200_kzg_witness_dev.argtypes = [vp, u64p, ctypes.c_size_t, u64p, u64p, u64p]
+        L.pb200_fr_horner_step_dev.argtypes = [vp, u64p, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]
         L.pb200_synthetic_bases_dev.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64]
         L.pb200_profile_enable.argtypes = [vp, ctypes.c_int]
         L.pb200_profile_ms.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_float)]
@@ -209,6 +215,26 @@ class Context:
         out = np.zeros(18, np.uint64)
         self._check(lib().pb200_g1_sum(self._h, _ptr(pts), pts.shape[0], _ptr(out)))
         return out
+
+    # -- KZG layer
+    def srs_generate(self, tau_mont, n):
+        tau = np.ascontiguousarray(tau_mont, dtype=np.uint64).reshape(4)
+        h = ctypes.c_void_p()
+        self._check(lib().pb200_srs_generate(self._h, _ptr(tau), n, ctypes.byref(h)))
+        return h
+
+    def srs_dev_ptr(self, srs):
+        return lib().pb200_srs_dev_ptr(srs)
+
+    def kzg_witness_dev(self, poly_dev, n, z_mont, quotient_dev):
+        z = np.ascontiguousarray(z_mont, dtype=np.uint64).reshape(4)
+        ev = np.zeros(4, np.uint64)
+        self._check(lib().pb200_kzg_witness_dev(self._h, ctypes.c_void_p(poly_dev), n, _ptr(z), ctypes.c_void_p(quotient_dev), _ptr(ev)))
+        return ev
+
+    def fr_horner_step_dev(self, acc_dev, n_acc, poly_dev, n_poly, c_mont):
+        c = np.ascontiguousarray(c_mont, dtype=np.uint64).reshape(4)
+        self._check(lib().pb200_fr_horner_step_dev(self._h, ctypes.c_void_p(acc_dev), n_acc, ctypes.c_void_p(poly_dev), n_poly, _ptr(c)))
 
     def synthetic_bases_dev(self, dev, n, a=0xB2000001, d=0x9E3779B1):
         self._check(lib().pb200_synthetic_bases_dev(self._h, ctypes.c_void_p(dev), n, a, d))
