@@ -143,6 +143,39 @@ PB200_API int pb200_kzg_witness_dev(pb200_ctx *ctx, const uint64_t *poly_dev, si
 PB200_API int pb200_fr_horner_step_dev(pb200_ctx *ctx, uint64_t *acc_dev, size_t n_acc, const uint64_t *poly_dev, size_t n_poly,
                                        const uint64_t c_mont[4]);
 
+/* ---- PLONK prover rounds above the hot path: dusk_plonk::proof_system::Prover --------- */
+typedef struct pb200_prover_key pb200_prover_key;
+/* The constraint system as StandardComposer holds it after circuit synthesis (the reference's gadgets,
+ * /root/reference/src/zk/gadgets.rs:28-225, only append rows to these vectors):  n_gates rows; 11 selector columns in
+ * the order q_m q_l q_r q_o q_c q_4 q_arith q_range q_logic q_fixed_group_add q_variable_group_add, each n_gates
+ * Montgomery scalars (NULL = all zero); 4 wire columns w_l w_r w_o w_4 holding the `Variable` index of each row. */
+typedef struct pb200_circuit {
+    size_t n_gates;
+    size_t n_vars;
+    const uint64_t *selectors[11];
+    const uint32_t *wires[4];
+} pb200_circuit;
+/* Prover::preprocess: pads to n = next power of two, interpolates and commits the 11 selector and 4 permutation
+ * polynomials (15 iNTT + 15 MSM), extends them to the 4n coset (15 coset NTTs), and seeds Transcript::new(label) with
+ * the verifier key.  Everything stays resident in HBM behind the returned handle.  vk_commitments (optional) receives
+ * the 15 compressed commitments in the column order above followed by left/right/out/fourth sigma.
+ * Only the arithmetic and range widgets are implemented: non-zero q_logic / q_fixed_group_add / q_variable_group_add
+ * columns are rejected (PB200_ERR_ARG). */
+PB200_API int pb200_preprocess(pb200_ctx *ctx, const pb200_srs *srs, const pb200_circuit *circuit, const uint8_t *transcript_label,
+                               size_t label_len, pb200_prover_key **out, uint8_t vk_commitments[15 * 48]);
+PB200_API void pb200_prover_key_free(pb200_ctx *ctx, pb200_prover_key *pk);
+PB200_API size_t pb200_prover_key_size(const pb200_prover_key *pk);  /* padded circuit size n */
+PB200_API size_t pb200_prover_key_bytes(const pb200_prover_key *pk); /* device memory held */
+/* Prover::prove_with_preprocessed + Proof::to_bytes: the witness is the value of every variable (n_vars Montgomery
+ * scalars, host), the public inputs a sparse (gate index, value) list.  Rounds 1-5 run on the device with the
+ * polynomials resident between rounds; the host hashes the transcript.  proof_out: 11 compressed G1 + 16 scalars.
+ * With profiling on, pb200_profile_ms knows "prove.round1" … "prove.round5" (host wall-clock per round). */
+PB200_API int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk, const uint64_t *values_mont,
+                          const uint32_t *pi_gate, const uint64_t *pi_mont, size_t n_pi, uint8_t proof_out[1040]);
+/* merlin::Transcript known-answer hook: Transcript::new(label); append_message(msg_label, msg); challenge_bytes(ch_label). */
+PB200_API int pb200_transcript_selftest(const char *label, const char *msg_label, const uint8_t *msg, size_t msg_len,
+                                        const char *challenge_label, uint8_t *out, size_t out_len);
+
 /* ---- synthetic workloads & measurement helpers (bench.py / tests) -------------- */
 /* bases[i] = (a + i·d)·G, packed affine Montgomery, written to a device buffer of n × 96 B. */
 PB200_API int pb200_synthetic_bases_dev(pb200_ctx *ctx, uint64_t *xy_mont_dev, size_t n, uint64_t a, uint64_t d);

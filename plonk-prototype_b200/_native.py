@@ -20,6 +20,8 @@ EXPORTS = [
     "pb200_srs_upload", "pb200_srs_wrap_dev", "pb200_srs_precompute", "pb200_srs_free", "pb200_srs_len",
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_g1_sum", "pb200_msm_window_bits",
     "pb200_srs_generate", "pb200_srs_dev_ptr", "pb200_kzg_witness_dev", "pb200_fr_horner_step_dev",
+    "pb200_preprocess", "pb200_prover_key_free", "pb200_prover_key_size", "pb200_prover_key_bytes", "pb200_prove",
+    "pb200_transcript_selftest",
     "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_launch_count",
     "pb200_imad_peak",
 ]
@@ -27,6 +29,12 @@ EXPORTS = [
 
 class Pb200Error(RuntimeError):
     pass
+
+
+class Circuit(ctypes.Structure):
+    """`pb200_circuit` (include/pb200.h)."""
+    _fields_ = [("n_gates", ctypes.c_size_t), ("n_vars", ctypes.c_size_t), ("selectors", ctypes.c_void_p * 11),
+                ("wires", ctypes.c_void_p * 4)]
 
 
 def lib():
@@ -77,6 +85,16 @@ def lib():
         L.pb200_srs_dev_ptr.restype = vp
         L.pb200_kzg_witness_dev.argtypes = [vp, u64p, ctypes.c_size_t, u64p, u64p, u64p]
         L.pb200_fr_horner_step_dev.argtypes = [vp, u64p, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]
+        L.pb200_preprocess.argtypes = [vp, vp, ctypes.POINTER(Circuit), ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), vp]
+        L.pb200_prover_key_free.argtypes = [vp, vp]
+        L.pb200_prover_key_free.restype = None
+        L.pb200_prover_key_size.argtypes = [vp]
+        L.pb200_prover_key_size.restype = ctypes.c_size_t
+        L.pb200_prover_key_bytes.argtypes = [vp]
+        L.pb200_prover_key_bytes.restype = ctypes.c_size_t
+        L.pb200_prove.argtypes = [vp, vp, vp, u64p, vp, u64p, ctypes.c_size_t, vp]
+        L.pb200_transcript_selftest.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
+                                                ctypes.c_char_p, ctypes.c_size_t]
         L.pb200_synthetic_bases_dev.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64]
         L.pb200_profile_enable.argtypes = [vp, ctypes.c_int]
         L.pb200_profile_ms.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_float)]
@@ -235,6 +253,50 @@ class Context:
     def fr_horner_step_dev(self, acc_dev, n_acc, poly_dev, n_poly, c_mont):
         c = np.ascontiguousarray(c_mont, dtype=np.uint64).reshape(4)
         self._check(lib().pb200_fr_horner_step_dev(self._h, ctypes.c_void_p(acc_dev), n_acc, ctypes.c_void_p(poly_dev), n_poly, _ptr(c)))
+
+    # -- PLONK prover rounds
+    def preprocess(self, srs, selectors, wires, n_vars, label):
+        """selectors: 11 (n_gates, 4) uint64 arrays or None; wires: 4 uint32 arrays.  Returns (key handle, 15×48 vk bytes)."""
+        keep = []
+        c = Circuit()
+        c.n_gates = len(wires[0])
+        c.n_vars = n_vars
+        for k in range(11):
+            if selectors[k] is None:
+                c.selectors[k] = None
+            else:
+                a = np.ascontiguousarray(selectors[k], dtype=np.uint64).reshape(-1, 4)
+                assert a.shape[0] == c.n_gates
+                keep.append(a)
+                c.selectors[k] = a.ctypes.data
+        for k in range(4):
+            a = np.ascontiguousarray(wires[k], dtype=np.uint32)
+            assert a.shape[0] == c.n_gates
+            keep.append(a)
+            c.wires[k] = a.ctypes.data
+        h = ctypes.c_void_p()
+        vk = np.zeros(15 * 48, np.uint8)
+        self._check(lib().pb200_preprocess(self._h, srs, ctypes.byref(c), bytes(label), len(label), ctypes.byref(h), _ptr(vk)))
+        return h, vk.tobytes()
+
+    def prover_key_free(self, pk):
+        lib().pb200_prover_key_free(self._h, pk)
+
+    def prover_key_size(self, pk):
+        return lib().pb200_prover_key_size(pk)
+
+    def prover_key_bytes(self, pk):
+        return lib().pb200_prover_key_bytes(pk)
+
+    def prove(self, srs, pk, values_mont, pi_gate, pi_mont):
+        vals = np.ascontiguousarray(values_mont, dtype=np.uint64).reshape(-1, 4)
+        pos = np.ascontiguousarray(pi_gate, dtype=np.uint32)
+        piv = np.ascontiguousarray(pi_mont, dtype=np.uint64).reshape(-1, 4)
+        assert pos.shape[0] == piv.shape[0]
+        out = np.zeros(1040, np.uint8)
+        self._check(lib().pb200_prove(self._h, srs, pk, _ptr(vals), _ptr(pos) if pos.size else None, _ptr(piv) if pos.size else None,
+                                      pos.shape[0], _ptr(out)))
+        return out.tobytes()
 
     def synthetic_bases_dev(self, dev, n, a=0xB2000001, d=0x9E3779B1):
         self._check(lib().pb200_synthetic_bases_dev(self._h, ctypes.c_void_p(dev), n, a, d))

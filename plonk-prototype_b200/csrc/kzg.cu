@@ -15,23 +15,11 @@
 #include <algorithm>
 #include <cstring>
 
+#include "fr_vec.cuh"
 #include "msm_common.cuh"
 
 namespace {
 
-__device__ __forceinline__ Fr ld_fr(const Fr *p) {
-    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-    uint4 a = q[0], b = q[1];
-    Fr r;
-    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
-    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
-    return r;
-}
-__device__ __forceinline__ void st_fr(Fr *p, const Fr &v) {
-    uint4 *q = reinterpret_cast<uint4 *>(p);
-    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
-}
 __device__ __forceinline__ G1Affine generator_affine() {  // G1 generator, Montgomery form
     const uint32_t gx[12] = {0xfd530c16u, 0x5cb38790u, 0x9976fff5u, 0x7817fc67u, 0x143ba1c1u, 0x154f95c7u,
                              0xf3d0e747u, 0xf0ae6acdu, 0x21dbf440u, 0xedce6eccu, 0x9e0bfb75u, 0x12017741u};

@@ -1,0 +1,174 @@
+"""Host-side mirror of the dusk-plonk 0.8.2 proving API the reference's circuits are written against
+(`StandardComposer`, `Prover`, `PublicParameters`; crate pinned at /root/reference/Cargo.toml:19; the composer
+calls mirrored here are exactly the ones /root/reference/src/zk/gadgets.rs:60-81,132,165,206-218 and
+circuits.rs:57,71 make — SURVEY.md App. C).
+
+Circuit synthesis is host-side bookkeeping in the reference too (it only appends rows to the composer's
+vectors), so it stays on the host here: Python ints for the witness values, numpy for the column images.
+Everything after synthesis — preprocessing and the five prover rounds — runs on the GPU behind
+`pb200_preprocess` / `pb200_prove` (csrc/plonk.cu).  There is no CPU proving path.
+"""
+import numpy as np
+
+from .domain import default_context
+
+R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+_MONT = (1 << 256) % R
+SELECTORS = ("q_m", "q_l", "q_r", "q_o", "q_c", "q_4", "q_arith", "q_range", "q_logic", "q_fixed_group_add",
+             "q_variable_group_add")
+
+
+def scalars_to_mont(values):
+    """Python ints (canonical, any sign) → (n, 4) uint64 Montgomery limbs, the ABI's scalar image."""
+    buf = b"".join(((v % R) * _MONT % R).to_bytes(32, "little") for v in values)
+    return np.frombuffer(buf, dtype="<u8").reshape(-1, 4).copy()
+
+
+class StandardComposer:
+    """Gate equation q_arith·(q_m·a·b + q_l·a + q_r·b + q_o·c + q_4·d + q_c) + PI = 0."""
+
+    def __init__(self):
+        self.q = {k: [] for k in SELECTORS}
+        self.w_l, self.w_r, self.w_o, self.w_4 = [], [], [], []
+        self.variables = []                 # Variable index → BlsScalar value (Python int)
+        self.public_inputs_sparse_store = {}
+        self.n = 0
+        self.zero_var = 0
+        self.zero_var = self.add_witness_to_circuit_description(0)
+        self.add_dummy_constraints()
+
+    def circuit_size(self):
+        return self.n
+
+    # ---- allocation
+    def add_input(self, s):
+        self.variables.append(s % R)
+        return len(self.variables) - 1
+
+    def _row(self, a, b, c, d, q_m=0, q_l=0, q_r=0, q_o=0, q_c=0, q_4=0, q_arith=1, q_range=0, pi=None):
+        row = dict(q_m=q_m, q_l=q_l, q_r=q_r, q_o=q_o, q_c=q_c, q_4=q_4, q_arith=q_arith, q_range=q_range)
+        for k in SELECTORS:
+            self.q[k].append(row.get(k, 0) % R)
+        self.w_l.append(a)
+        self.w_r.append(b)
+        self.w_o.append(c)
+        self.w_4.append(d)
+        if pi is not None:
+            self.public_inputs_sparse_store[self.n] = pi % R
+        self.n += 1
+
+    # ---- the calls the reference's gadgets make
+    def poly_gate(self, a, b, c, q_m, q_l, q_r, q_o, q_c, pi=None):
+        self._row(a, b, c, self.zero_var, q_m=q_m, q_l=q_l, q_r=q_r, q_o=q_o, q_c=q_c, pi=pi)
+        return a, b, c
+
+    def add(self, q_l_a, q_r_b, q_c, pi=None):
+        (q_l, a), (q_r, b) = q_l_a, q_r_b
+        c = self.add_input(q_l * self.variables[a] + q_r * self.variables[b] + q_c + (pi or 0))
+        self._row(a, b, c, self.zero_var, q_l=q_l, q_r=q_r, q_o=-1, q_c=q_c, pi=pi)
+        return c
+
+    def mul(self, q_m, a, b, q_c, pi=None):
+        c = self.add_input(q_m * self.variables[a] * self.variables[b] + q_c + (pi or 0))
+        self._row(a, b, c, self.zero_var, q_m=q_m, q_o=-1, q_c=q_c, pi=pi)
+        return c
+
+    def add_gate(self, a, b, c, q_l, q_r, q_o, q_c, pi=None):
+        self._row(a, b, c, self.zero_var, q_l=q_l, q_r=q_r, q_o=q_o, q_c=q_c, pi=pi)
+        return c
+
+    def mul_gate(self, a, b, c, q_m, q_o, q_c, pi=None):
+        self._row(a, b, c, self.zero_var, q_m=q_m, q_o=q_o, q_c=q_c, pi=pi)
+        return c
+
+    def boolean_gate(self, a):
+        self._row(a, a, a, self.zero_var, q_m=1, q_o=-1)
+        return a
+
+    def constrain_to_constant(self, a, constant, pi=None):
+        self._row(a, a, a, self.zero_var, q_l=1, q_c=-constant, pi=pi)
+
+    def assert_equal(self, a, b):
+        self._row(a, b, self.zero_var, self.zero_var, q_l=1, q_r=-1)
+
+    def add_witness_to_circuit_description(self, value):
+        var = self.add_input(value)
+        self.constrain_to_constant(var, value, None)
+        return var
+
+    def range_rows(self, a, b, c, d):
+        """One row of the range widget (q_range = 1): quads c−4d, b−4c, a−4b, d_next−4a ∈ {0,1,2,3}."""
+        self._row(a, b, c, d, q_arith=0, q_range=1)
+
+    def add_dummy_constraints(self):
+        six, one, seven, m20 = (self.add_input(v) for v in (6, 1, 7, -20))
+        self._row(six, seven, m20, one, q_m=1, q_l=2, q_r=3, q_o=4, q_c=4, q_4=1)
+        self._row(m20, six, seven, self.zero_var, q_m=1, q_l=1, q_r=1, q_o=1, q_c=127)
+
+    # ---- column images for the ABI
+    def selector_columns(self):
+        out = []
+        for k in SELECTORS:
+            col = self.q[k]
+            out.append(scalars_to_mont(col) if any(col) else None)
+        return out
+
+    def wire_columns(self):
+        return [np.asarray(w, dtype=np.uint32) for w in (self.w_l, self.w_r, self.w_o, self.w_4)]
+
+
+class PublicParameters:
+    """`PublicParameters::setup(max_degree, rng)` with the trapdoor supplied by the caller (test / benchmark SRS):
+    powers_of_g[i] = τ^i·G generated on the device and kept resident, pre-doubled window copies for fast commits."""
+
+    def __init__(self, max_degree, tau, ctx=None, precompute=True):
+        self.ctx = ctx or default_context()
+        self.n_points = max_degree + 1
+        self.srs = self.ctx.srs_generate(scalars_to_mont([tau]), self.n_points)
+        if precompute and self.n_points <= (1 << 22):
+            self.ctx.srs_precompute(self.srs)
+
+    def close(self):
+        if self.srs is not None:
+            self.ctx.srs_free(self.srs)
+            self.srs = None
+
+
+class Prover:
+    """`Prover::new(label)`, `.mut_cs()`, `.preprocess(&ck)`, `.prove(&ck)`."""
+
+    def __init__(self, label, ctx=None):
+        self.label = bytes(label)
+        self.cs = StandardComposer()
+        self.ctx = ctx or default_context()
+        self._pk = None
+        self.verifier_key_bytes = None
+
+    def mut_cs(self):
+        return self.cs
+
+    def circuit_size(self):
+        return self.cs.circuit_size()
+
+    def preprocess(self, pp):
+        if self._pk is not None:
+            raise RuntimeError("CircuitAlreadyPreprocessed")
+        self._pk, self.verifier_key_bytes = self.ctx.preprocess(pp.srs, self.cs.selector_columns(), self.cs.wire_columns(),
+                                                                len(self.cs.variables), self.label)
+        self.padded_size = self.ctx.prover_key_size(self._pk)
+
+    def prove(self, pp, variables=None):
+        """Returns `Proof::to_bytes()` (1040 bytes).  `variables` overrides the composer's assignment (same circuit,
+        new witness) as (n_vars, 4) Montgomery limbs."""
+        if self._pk is None:
+            self.preprocess(pp)
+        vals = variables if variables is not None else scalars_to_mont(self.cs.variables)
+        pis = sorted(self.cs.public_inputs_sparse_store.items())
+        pos = np.asarray([p for p, _ in pis], dtype=np.uint32)
+        piv = scalars_to_mont([v for _, v in pis]) if pis else np.zeros((0, 4), np.uint64)
+        return self.ctx.prove(pp.srs, self._pk, vals, pos, piv)
+
+    def close(self):
+        if self._pk is not None:
+            self.ctx.prover_key_free(self._pk)
+            self._pk = None

@@ -1,0 +1,135 @@
+"""CPU tests of the protocol layer above the hot path: the pure-Python model (oracle/plonk_model.py) against its
+external anchors and committed golden proofs, and the host-side pieces of the product (Merlin transcript in
+libpb200.so, StandardComposer mirror).  No GPU compute here."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import model
+import plonk_model as pm
+from helpers import load_golden
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+import gen_plonk_golden as gen  # noqa: E402
+
+MERLIN_KAT = "d5a21972d0d5fe320c0d263fac7fffb8145aa640af6e9bca177c03c7efcf0615"
+
+
+def test_merlin_known_answer_model():
+    """merlin's own `equivalence_simple` vector."""
+    t = pm.Transcript(b"test protocol")
+    t.append_message(b"some label", b"some data")
+    assert t.challenge_bytes(b"challenge", 32).hex() == MERLIN_KAT
+
+
+def test_merlin_known_answer_library():
+    """The host transcript compiled into libpb200.so (csrc/merlin.h) — loads the library, needs no GPU."""
+    import plonk_prototype_b200 as pb
+    from plonk_prototype_b200 import _native
+    out = ctypes.create_string_buffer(32)
+    rc = _native.lib().pb200_transcript_selftest(b"test protocol", b"some label", b"some data", 9, b"challenge", out, 32)
+    assert rc == 0 and out.raw.hex() == MERLIN_KAT
+    # a multi-block squeeze and absorb (crosses the 166-byte STROBE rate) against the model
+    msg = bytes(range(256)) * 3
+    out = ctypes.create_string_buffer(400)
+    assert _native.lib().pb200_transcript_selftest(b"pb200", b"blob", msg, len(msg), b"long", out, 400) == 0
+    t = pm.Transcript(b"pb200")
+    t.append_message(b"blob", msg)
+    assert t.challenge_bytes(b"long", 400) == out.raw
+
+
+def test_g2_generator_and_pairing():
+    assert pm.g2_on_curve(pm.G2_GEN) and pm.g2_mul(pm.G2_GEN, model.R) is None
+    a, b = 0x1234567, 0x89ABCDEF01
+    e_ab = pm.final_exponentiation(pm.miller_loop(model.g1_mul(model.G1_GEN, a), pm.g2_mul(pm.G2_GEN, b)))
+    e = pm.final_exponentiation(pm.miller_loop(model.G1_GEN, pm.G2_GEN))
+    assert e != pm.F12_ONE and e_ab == pm.f12_pow(e, a * b % model.R)
+    assert pm.f12_pow(e, model.R) == pm.F12_ONE
+    # e(aG, H)·e(−G, aH) = 1: the shape of the KZG check
+    assert pm.pairing_product_is_one([(model.g1_mul(model.G1_GEN, a), pm.G2_GEN),
+                                      (model.g1_neg(model.G1_GEN), pm.g2_mul(pm.G2_GEN, a))])
+
+
+def test_sigma_permutation_is_a_permutation_with_variable_cycles():
+    comp = pm.synthetic_circuit(13)
+    sig = pm.sigma_positions(comp.w, 16)
+    flat = [p for col in sig for p in col]
+    assert sorted(flat) == [(c, i) for c in range(4) for i in range(16)]
+    for c in range(4):
+        for i in range(comp.n):
+            c2, i2 = sig[c][i]
+            assert comp.w[c2][i2] == comp.w[c][i]      # stays on the same variable
+        for i in range(comp.n, 16):
+            assert sig[c][i] == (c, i)                  # identity on padding
+
+
+def test_model_reproduces_golden_proof_and_verifier_rejects_tampering():
+    g = load_golden("plonk_kat.json")
+    case = g["cases"][0]
+    tau, label = int(g["tau"], 16), g["label"].encode()
+    comp = pm.synthetic_circuit(case["n_gates"])
+    ck = pm.srs_setup(tau, case["n"])
+    pk, vk, tr = pm.preprocess(comp, ck, label)
+    _, pb = pm.prove(comp, pk, ck, tr)
+    assert pb.hex() == case["proof"]
+    ok = pm.opening_key(tau)
+    assert pm.verify(vk, pb, comp.pi, ok, label)
+    bad = bytearray(pb)
+    bad[700] ^= 0x01                                      # one evaluation bit
+    assert not pm.verify(vk, bytes(bad), comp.pi, ok, label)
+    wrong_pi = {k: (v + 1) % model.R for k, v in comp.pi.items()}
+    assert not pm.verify(vk, pb, wrong_pi, ok, label)
+    assert not pm.verify(vk, pb, comp.pi, ok, b"another transcript")
+
+
+def test_unsatisfied_circuit_does_not_verify():
+    comp = pm.synthetic_circuit(13)
+    comp.values[comp.w[2][5]] = (comp.values[comp.w[2][5]] + 1) % model.R   # break one gate
+    assert not comp.check()
+    tau, label = 0xABCDEF, b"x"
+    ck = pm.srs_setup(tau, 16)
+    pk, vk, tr = pm.preprocess(comp, ck, label)
+    _, pb = pm.prove(comp, pk, ck, tr)
+    assert not pm.verify(vk, pb, comp.pi, pm.opening_key(tau), label)
+
+
+def test_product_composer_matches_model_composer():
+    """The shipped StandardComposer mirror and the model composer build identical columns from the gadget calls the
+    reference makes (gadgets.rs:49-84 `maybe_equal`, :120-135 `min_bound`, boolean decomposition :210-220)."""
+    import plonk_prototype_b200 as pb
+
+    def build(c, pi_none):
+        a, b = c.add_input(1234), c.add_input(1200)
+        u = c.add((1, a), (-1, b), 0, pi_none)
+        zinv = c.add_input(pow(34, -1, model.R))
+        y = c.mul(-1, zinv, u, 1, pi_none)
+        c.mul_gate(y, u, u, 1, 0, 0, pi_none)
+        bits = [c.add_input((34 >> k) & 1) for k in range(8)]
+        acc = c.add_witness_to_circuit_description(0)
+        for k, bit in enumerate(bits):
+            c.boolean_gate(bit)
+            acc = c.add((1 << k, bit), (1, acc), 0, pi_none)
+        c.constrain_to_constant(acc, 0, -34)
+        return c
+
+    m = build(pm.Composer(), 0)
+    p = build(pb.StandardComposer(), None)
+    assert m.check()
+    assert p.n == m.n and p.variables == m.values
+    assert [list(x) for x in (p.w_l, p.w_r, p.w_o, p.w_4)] == m.w
+    for k in pm.SELECTORS:
+        assert p.q[k] == m.q[k], k
+    assert {k: v for k, v in p.public_inputs_sparse_store.items() if v} == m.pi
+    cols = p.selector_columns()
+    assert cols[pm.SELECTORS.index("q_logic")] is None
+    want = np.array([model.to_limbs(model.fr_to_mont(v), 4) for v in m.q["q_c"]], dtype=np.uint64)
+    assert (cols[pm.SELECTORS.index("q_c")] == want).all()
+
+
+def test_range_circuit_model():
+    comp = gen.range_circuit(0xB2C7, 16)
+    assert comp.check()
+    assert any(comp.q["q_range"])

@@ -1,0 +1,185 @@
+"""GPU parity tests of the KZG layer and the prover rounds (csrc/kzg.cu, csrc/plonk.cu) through the C ABI, against
+the pure-Python protocol model: byte-identical proofs and verifier keys on the committed golden circuits, and —
+at sizes the model cannot prove — acceptance by the model's pairing verifier plus rejection after tampering."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import model
+import plonk_model as pm
+from helpers import load_golden
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+import gen_plonk_golden as gen  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def mont(vals):
+    import plonk_prototype_b200 as pb
+    return pb.scalars_to_mont(vals)
+
+
+def columns(comp):
+    sel = [mont(comp.q[k]) if any(comp.q[k]) else None for k in pm.SELECTORS]
+    wires = [np.asarray(w, dtype=np.uint32) for w in comp.w]
+    return sel, wires
+
+
+def gpu_prove(ctx, comp, tau, label):
+    """Preprocess + prove the model composer's circuit on the GPU.  Returns (proof bytes, vk bytes)."""
+    import plonk_prototype_b200 as pb
+    n = pm.domain(comp.n)["size"]
+    pp = pb.PublicParameters(n - 1, tau, ctx)
+    try:
+        sel, wires = columns(comp)
+        pk, vk = ctx.preprocess(pp.srs, sel, wires, len(comp.values), label)
+        try:
+            pis = sorted(comp.pi.items())
+            proof = ctx.prove(pp.srs, pk, mont(comp.values), np.asarray([p for p, _ in pis], dtype=np.uint32),
+                              mont([v for _, v in pis]) if pis else np.zeros((0, 4), np.uint64))
+            again = ctx.prove(pp.srs, pk, mont(comp.values), np.asarray([p for p, _ in pis], dtype=np.uint32),
+                              mont([v for _, v in pis]) if pis else np.zeros((0, 4), np.uint64))
+            assert again == proof                      # no prover blinding in 0.8.x: proving is deterministic
+        finally:
+            ctx.prover_key_free(pk)
+    finally:
+        pp.close()
+    return proof, vk
+
+
+def vk_from_bytes(vkb, n):
+    pts = [pm.bytes_to_g1(vkb[48 * i:48 * i + 48]) for i in range(15)]
+    return {"n": n, "q": dict(zip(pm.SELECTORS, pts[:11])), "sigma": pts[11:]}
+
+
+def golden_circuit(case):
+    if case["name"] == "synthetic_13":
+        return pm.synthetic_circuit(13)
+    if case["name"] == "synthetic_30":
+        return pm.synthetic_circuit(30, seed=0x77, n_pub=3)
+    if case["name"] == "range_16bit":
+        return gen.range_circuit(0xB2C7, 16)
+    raise KeyError(case["name"])
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_golden_proofs_byte_identical(ctx, idx):
+    g = load_golden("plonk_kat.json")
+    case = g["cases"][idx]
+    comp = golden_circuit(case)
+    proof, vk = gpu_prove(ctx, comp, int(g["tau"], 16), g["label"].encode())
+    assert vk.hex() == case["vk"]
+    assert proof.hex() == case["proof"]
+
+
+@pytest.mark.parametrize("n_gates", [100, 1000, 5000, (1 << 14) - 3])
+def test_proof_accepted_by_pairing_verifier(ctx, n_gates):
+    tau, label = 0x5EED0000 + n_gates, b"pb200-verify"
+    comp = pm.synthetic_circuit(n_gates, seed=n_gates)
+    proof, vkb = gpu_prove(ctx, comp, tau, label)
+    n = pm.domain(comp.n)["size"]
+    vk = vk_from_bytes(vkb, n)
+    ok = pm.opening_key(tau)
+    assert pm.verify(vk, proof, comp.pi, ok, label)
+    bad = bytearray(proof)
+    bad[528 + 5] ^= 0x10                                   # a_eval
+    assert not pm.verify(vk, bytes(bad), comp.pi, ok, label)
+    bad = bytearray(proof)
+    bad[48 * 4 + 20] ^= 0x01                               # z_comm (almost surely not a curve point any more)
+    assert not pm.verify(vk, bytes(bad), comp.pi, ok, label)
+    wrong_pi = dict(comp.pi)
+    k = next(iter(wrong_pi))
+    wrong_pi[k] = (wrong_pi[k] + 1) % model.R
+    assert not pm.verify(vk, proof, wrong_pi, ok, label)
+
+
+def test_bad_witness_is_rejected_by_verifier(ctx):
+    tau, label = 0xBAD, b"pb200-verify"
+    comp = pm.synthetic_circuit(200)
+    comp.values[comp.w[2][50]] = (comp.values[comp.w[2][50]] + 1) % model.R
+    proof, vkb = gpu_prove(ctx, comp, tau, label)
+    assert not pm.verify(vk_from_bytes(vkb, 256), proof, comp.pi, pm.opening_key(tau), label)
+
+
+def test_prover_mirror_api(ctx):
+    """The dusk-plonk-shaped Python surface: Prover::new(label) / mut_cs() gadgets / preprocess / prove."""
+    import plonk_prototype_b200 as pb
+    tau, label = 0xC0FFEE, b"mirror"
+    pp = pb.PublicParameters(63, tau, ctx)
+    prover = pb.Prover(label, ctx)
+    cs = prover.mut_cs()
+    a, b = cs.add_input(20), cs.add_input(22)
+    s = cs.add((1, a), (1, b), 0, None)
+    cs.constrain_to_constant(s, 0, -42)                      # public input: the sum
+    for bit in (0, 1, 0, 1):
+        cs.boolean_gate(cs.add_input(bit))
+    prover.preprocess(pp)
+    proof = prover.prove(pp)
+    vk = vk_from_bytes(prover.verifier_key_bytes, prover.padded_size)
+    pi = {k: v for k, v in cs.public_inputs_sparse_store.items()}
+    assert pm.verify(vk, proof, pi, pm.opening_key(tau), label)
+    with pytest.raises(RuntimeError):
+        prover.preprocess(pp)
+    prover.close()
+    pp.close()
+
+
+def test_unsupported_widget_is_rejected_loudly(ctx):
+    import plonk_prototype_b200 as pb
+    comp = pm.synthetic_circuit(13)
+    sel, wires = columns(comp)
+    sel[pm.SELECTORS.index("q_logic")] = mont([1] * comp.n)
+    pp = pb.PublicParameters(15, 5, ctx)
+    with pytest.raises(pb.Pb200Error):
+        ctx.preprocess(pp.srs, sel, wires, len(comp.values), b"x")
+    pp.close()
+
+
+# ---------------------------------------------------------------------------------------------- KZG layer
+def test_srs_generate_matches_model(ctx, oracle):
+    tau, n = 0x1234567890ABCDEF1234567, 300
+    srs = ctx.srs_generate(mont([tau]), n)
+    host = np.zeros((n, 12), np.uint64)
+    ctx.d2h(host, ctx.srs_dev_ptr(srs))
+    ctx.srs_free(srs)
+    want = pm.srs_setup(tau, n)
+    for i in (0, 1, 2, 17, 255, 256, 299):
+        x = model.fp_from_mont(model.from_limbs(host[i, :6]))
+        y = model.fp_from_mont(model.from_limbs(host[i, 6:]))
+        assert (x, y) == want[i], i
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 1024, 1025, 5000])
+def test_kzg_witness_matches_ruffini(ctx, n):
+    coeffs = model.random_fr(0x6B7A + n, n)
+    z = model.random_fr(0x2222, 1)[0]
+    p_dev, q_dev = ctx.malloc(32 * n), ctx.malloc(32 * n)
+    for point in (z, 0, 1):
+        ctx.h2d(p_dev, mont(coeffs))
+        ev = ctx.kzg_witness_dev(p_dev, n, mont([point])[0], q_dev)
+        got = np.zeros((n, 4), np.uint64)
+        ctx.d2h(got, q_dev)
+        want = pm.ruffini(coeffs, point) + [0]
+        assert (got == mont(want)).all()
+        assert (ev == mont([pm.poly_eval(coeffs, point)])[0]).all()
+    ctx.free(p_dev)
+    ctx.free(q_dev)
+
+
+def test_fr_horner_step(ctx):
+    n, m = 1000, 700
+    acc, p = model.random_fr(1, n), model.random_fr(2, m)
+    c = model.random_fr(3, 1)[0]
+    a_dev, p_dev = ctx.malloc(32 * n), ctx.malloc(32 * m)
+    ctx.h2d(a_dev, mont(acc))
+    ctx.h2d(p_dev, mont(p))
+    ctx.fr_horner_step_dev(a_dev, n, p_dev, m, mont([c])[0])
+    got = np.zeros((n, 4), np.uint64)
+    ctx.d2h(got, a_dev)
+    want = [(acc[j] * c + (p[j] if j < m else 0)) % model.R for j in range(n)]
+    assert (got == mont(want)).all()
+    ctx.free(a_dev)
+    ctx.free(p_dev)
