@@ -607,3 +607,6 @@ ORC_API int orc_domain(uint32_t log_n, uint64_t *group_gen, uint64_t *group_gen_
     memcpy(generator_inv, seven_inv.l, 32);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------ PLONK prover restatement */
+#include "plonk_oracle.inc"

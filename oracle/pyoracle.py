@@ -17,7 +17,7 @@ _U64P = ctypes.POINTER(ctypes.c_uint64)
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    src = [os.path.join(_HERE, f) for f in ("oracle.c", "mont.h", "mont_asm.h", "Makefile")]
+    src = [os.path.join(_HERE, f) for f in ("oracle.c", "plonk_oracle.inc", "mont.h", "mont_asm.h", "Makefile")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
     return so
@@ -163,3 +163,58 @@ def int_to_limbs(v, n):
 
 def ints_to_limbs(vals, n):
     return np.array([[(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)] for v in vals], dtype=np.uint64).reshape(-1, n)
+
+
+# ----------------------------------------------------------------------------- PLONK prover restatement
+def merlin_selftest(label, msg_label, msg, ch_label, n):
+    out = ctypes.create_string_buffer(n)
+    lib().orc_merlin_selftest(label, msg_label, msg, ctypes.c_size_t(len(msg)), ch_label, out, ctypes.c_size_t(n))
+    return out.raw
+
+
+def srs_setup(tau_mont, n):
+    """powers_of_g[i] = τ^i·G as packed affine Montgomery points (n, 12) — small n (one scalar mul each)."""
+    tau = np.ascontiguousarray(tau_mont, dtype=np.uint64).reshape(4)
+    out = np.empty((n, 12), np.uint64)
+    lib().orc_srs_setup(_p(tau), ctypes.c_size_t(n), _p(out))
+    return out
+
+
+def plonk_prove(selectors, wires, values_mont, pi_pos, pi_mont, srs, label, threads=1):
+    """Preprocess + prove on the CPU.  selectors: 11 (n_gates, 4) uint64 arrays or None; wires: 4 uint32 arrays;
+    srs: (≥ n_pad, 12) packed affine points.  Returns (proof bytes, vk bytes, preprocess seconds, prove seconds)."""
+    n_gates = len(wires[0])
+    keep = []
+    sel_arr = (ctypes.c_void_p * 11)()
+    for k in range(11):
+        if selectors[k] is None:
+            sel_arr[k] = None
+        else:
+            a = np.ascontiguousarray(selectors[k], dtype=np.uint64).reshape(-1, 4)
+            assert a.shape[0] == n_gates
+            keep.append(a)
+            sel_arr[k] = a.ctypes.data
+    w_arr = (ctypes.c_void_p * 4)()
+    for k in range(4):
+        a = np.ascontiguousarray(wires[k], dtype=np.uint32)
+        keep.append(a)
+        w_arr[k] = a.ctypes.data
+    vals = np.ascontiguousarray(values_mont, dtype=np.uint64).reshape(-1, 4)
+    pos = np.ascontiguousarray(pi_pos, dtype=np.uint32)
+    piv = np.ascontiguousarray(pi_mont, dtype=np.uint64).reshape(-1, 4)
+    srs = np.ascontiguousarray(srs, dtype=np.uint64).reshape(-1, 12)
+    n_pad = 1
+    while n_pad < n_gates:
+        n_pad *= 2
+    assert srs.shape[0] >= n_pad
+    vk = ctypes.create_string_buffer(15 * 48)
+    proof = ctypes.create_string_buffer(1040)
+    tm = (ctypes.c_double * 2)()
+    f = lib().orc_plonk_prove
+    f.restype = ctypes.c_int
+    rc = f(ctypes.c_size_t(n_gates), ctypes.c_size_t(vals.shape[0]), sel_arr, w_arr, ctypes.c_void_p(vals.ctypes.data),
+           ctypes.c_void_p(pos.ctypes.data), ctypes.c_void_p(piv.ctypes.data), ctypes.c_size_t(pos.shape[0]),
+           ctypes.c_void_p(srs.ctypes.data), bytes(label), ctypes.c_size_t(len(label)), ctypes.c_int(threads), vk, proof, tm)
+    if rc != 0:
+        raise RuntimeError("orc_plonk_prove failed: %d" % rc)
+    return proof.raw, vk.raw, tm[0], tm[1]

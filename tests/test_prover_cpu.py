@@ -133,3 +133,46 @@ def test_range_circuit_model():
     comp = gen.range_circuit(0xB2C7, 16)
     assert comp.check()
     assert any(comp.q["q_range"])
+
+
+# ---------------------------------------------------------------------------------------------- C restatement
+def _mont(oracle, vals):
+    return oracle.fr_to_mont(oracle.ints_to_limbs([v % model.R for v in vals], 4))
+
+
+def c_oracle_prove(oracle, comp, tau, label, threads=1, srs=None):
+    n = pm.domain(comp.n)["size"]
+    if srs is None:
+        srs = oracle.srs_setup(_mont(oracle, [tau])[0], n)
+    sel = [_mont(oracle, comp.q[k]) if any(comp.q[k]) else None for k in pm.SELECTORS]
+    wires = [np.asarray(w, dtype=np.uint32) for w in comp.w]
+    pis = sorted(comp.pi.items())
+    proof, vk, _, _ = oracle.plonk_prove(sel, wires, _mont(oracle, comp.values), np.asarray([p for p, _ in pis], dtype=np.uint32),
+                                        _mont(oracle, [v for _, v in pis]) if pis else np.zeros((0, 4), np.uint64), srs, label,
+                                        threads=threads)
+    return proof, vk
+
+
+def test_c_oracle_merlin_known_answer(oracle):
+    assert oracle.merlin_selftest(b"test protocol", b"some label", b"some data", b"challenge", 32).hex() == MERLIN_KAT
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_c_oracle_prover_reproduces_golden_proofs(oracle, threads):
+    """The C restatement (the CPU baseline bench.py times) is byte-identical with the big-int model."""
+    g = load_golden("plonk_kat.json")
+    tau, label = int(g["tau"], 16), g["label"].encode()
+    circuits = [pm.synthetic_circuit(13), pm.synthetic_circuit(30, seed=0x77, n_pub=3), gen.range_circuit(0xB2C7, 16)]
+    for case, comp in zip(g["cases"], circuits):
+        proof, vk = c_oracle_prove(oracle, comp, tau, label, threads)
+        assert vk.hex() == case["vk"], case["name"]
+        assert proof.hex() == case["proof"], case["name"]
+
+
+def test_c_oracle_proof_verifies_at_2k_gates(oracle):
+    tau, label = 0x7A5, b"c-oracle"
+    comp = pm.synthetic_circuit(2000, seed=9)
+    proof, vkb = c_oracle_prove(oracle, comp, tau, label, threads=8)
+    pts = [pm.bytes_to_g1(vkb[48 * i:48 * i + 48]) for i in range(15)]
+    vk = {"n": 2048, "q": dict(zip(pm.SELECTORS, pts[:11])), "sigma": pts[11:]}
+    assert pm.verify(vk, proof, comp.pi, pm.opening_key(tau), label)

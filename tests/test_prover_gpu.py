@@ -96,6 +96,40 @@ def test_proof_accepted_by_pairing_verifier(ctx, n_gates):
     assert not pm.verify(vk, proof, wrong_pi, ok, label)
 
 
+@pytest.mark.parametrize("n_gates", [1 << 10, 5000])
+def test_proof_byte_identical_with_c_restatement(ctx, oracle, n_gates):
+    """Whole proofs at sizes the Python model cannot reach: the CUDA prover against the C restatement of the upstream
+    prover (oracle/plonk_oracle.inc) on the same circuit, witness and SRS."""
+    from test_prover_cpu import c_oracle_prove
+    tau, label = 0xFEED + n_gates, b"pb200-c-parity"
+    comp = pm.synthetic_circuit(n_gates, seed=3 * n_gates)
+    proof, vk = gpu_prove(ctx, comp, tau, label)
+    want_proof, want_vk = c_oracle_prove(oracle, comp, tau, label, threads=8)
+    assert vk == want_vk
+    assert proof == want_proof
+
+
+def test_full_size_proof_2_20_gates_accepted_by_pairing_verifier(ctx):
+    """BASELINE.json configs[3] at full size: the verifier's cost does not depend on the circuit size, so the 2^20-gate
+    proof is checked by the same pairing verifier (size-independent property)."""
+    import plonk_prototype_b200 as pb
+    from plonk_prototype_b200.synth import synthetic_circuit_columns
+    L, tau, label = 20, 0xB2000014, b"pb200-full"
+    n = 1 << L
+    sel, wires, values, pi_pos, pi_vals = synthetic_circuit_columns(n)
+    pp = pb.PublicParameters(n - 1, tau, ctx)
+    pk, vkb = ctx.preprocess(pp.srs, sel, wires, values.shape[0], label)
+    proof = ctx.prove(pp.srs, pk, values, pi_pos, pi_vals)
+    ctx.prover_key_free(pk)
+    pp.close()
+    rinv = pow(model.FR_MONT_R, -1, model.R)
+    pi = {int(p): model.from_limbs(v) * rinv % model.R for p, v in zip(pi_pos, pi_vals)}
+    assert pm.verify(vk_from_bytes(vkb, n), proof, pi, pm.opening_key(tau), label)
+    bad = bytearray(proof)
+    bad[1039] ^= 0x01
+    assert not pm.verify(vk_from_bytes(vkb, n), bytes(bad), pi, pm.opening_key(tau), label)
+
+
 def test_bad_witness_is_rejected_by_verifier(ctx):
     tau, label = 0xBAD, b"pb200-verify"
     comp = pm.synthetic_circuit(200)
