@@ -120,6 +120,13 @@ PB200_API int pb200_msm_g1(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, 
 /* Same with scalars already on the DEVICE (n × 32 B).  Blocks; result on the host. */
 PB200_API int pb200_msm_g1_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_mont_dev, size_t n,
                      uint64_t out_xyz_mont[18]);
+/* `batch` MSMs over the SAME bases in one pass — the shape of a prover round (four wire commitments, four quotient
+ * parts, two opening witnesses): scalar vector j starts at scalars_mont_dev + 4·j·scalar_stride (scalar_stride ≥ n, in
+ * scalars) and out_xyz_mont receives batch × 18 u64.  With pre-doubled copies (pb200_srs_precompute) every vector gets
+ * its own bucket set and the sort, accumulation and reduction run once for all of them; otherwise the calls are made
+ * one after the other.  Blocks; results on the host. */
+PB200_API int pb200_msm_g1_batch_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_mont_dev, size_t n,
+                                     uint32_t batch, size_t scalar_stride, uint64_t *out_xyz_mont);
 /* Sum of `count` projective points (each X ‖ Y ‖ Z, 18 × u64 Montgomery, HOST memory) — the combine step after
  * a point-range-sharded MSM: every rank's partial result is gathered and added here.
  * Output as for pb200_msm_g1. */

@@ -262,6 +262,19 @@ struct Field {
         }
         return r;
     }
+    // this^e for a 32-bit exponent, looping over the significant bits only (index-dependent powers z^j in the
+    // vector kernels: ≈ log2(j) squarings instead of 64).
+    PB_HD Field pow_u32(uint32_t e) const {
+        if (e == 0) return one();
+        int top = 31;
+        while (!((e >> top) & 1)) top--;
+        Field r = *this;
+        for (int i = top - 1; i >= 0; i--) {
+            r = r.sqr();
+            if ((e >> i) & 1) r = r * *this;
+        }
+        return r;
+    }
     PB_HD Field pow_u64(uint64_t e) const {
         uint32_t w[2] = {(uint32_t)e, (uint32_t)(e >> 32)};
         return pow(w, 2);

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(128) srs_table_kernel(const G1Affine *bases32,
 __global__ void __launch_bounds__(128) srs_powers_kernel(const G1Affine *__restrict__ table, const Fr *tau, uint32_t n, G1Affine *out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const Fr s = ld_fr(tau).pow_u64(i).from_mont();
+    const Fr s = ld_fr(tau).pow_u32(i).from_mont();
     G1Xyzz acc = G1Xyzz::identity();
     for (uint32_t w = 0; w < 32; w++) {
         const uint32_t d = (s.l[w >> 2] >> (8 * (w & 3))) & 0xff;
@@ -87,11 +87,16 @@ __global__ void witness_consts_kernel(const Fr *z, Fr *consts) {
     st_fr(consts + 1, v.inv());
     st_fr(consts + 2, Fr::one());
 }
-// b[j] = a[j]·z^j
+// b[j] = a[j]·z^j, four consecutive j per thread (one power by square-and-multiply, then running products)
 __global__ void witness_scale_kernel(const Fr *a, Fr *b, uint32_t n, const Fr *consts) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    st_fr(b + j, ld_fr(a + j) * ld_fr(consts + 0).pow_u64(j));
+    const uint32_t j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= n) return;
+    const Fr z = ld_fr(consts + 0);
+    Fr p = z.pow_u32(j0);
+    for (uint32_t k = 0; k < 4 && j0 + k < n; k++) {
+        st_fr(b + j0 + k, ld_fr(a + j0 + k) * p);
+        p = p * z;
+    }
 }
 // Suffix sums over Fr in three kernels (tiles of 1024 elements, 256 threads × 4).  S[i] = Σ_{j ≥ i} b[j].
 constexpr uint32_t kFrScanTile = 1024;
@@ -152,9 +157,12 @@ __global__ void __launch_bounds__(256) witness_finish_kernel(const Fr *b, uint32
     Fr inc = block_suffix_scan(s, sm, nullptr);
     Fr run = (inc - s) + ld_fr(tile_sums + blockIdx.x);  // Σ of everything after this thread's four elements
     const Fr zinv = ld_fr(consts + 1);
+    Fr zi[4];  // z^{−(base+k+1)}
+    zi[0] = zinv.pow_u32(base + 1);
+    for (int k = 1; k < 4; k++) zi[k] = zi[k - 1] * zinv;
     for (int k = 3; k >= 0; k--) {
         // run = S[base+k+1]
-        if (base + k < n) st_fr(q + base + k, run * zinv.pow_u64((uint64_t)base + k + 1));
+        if (base + k < n) st_fr(q + base + k, run * zi[k]);
         run = run + v[k];
     }
 }
@@ -241,7 +249,7 @@ extern "C" int pb200_kzg_witness_dev(pb200_ctx *ctx, const uint64_t *poly_dev, s
         witness_consts_kernel<<<1, 1, 0, st>>>(zd, consts);
         PB_LAUNCHED(ctx);
         // b = a·z^j is staged in the quotient buffer, the finishing pass reads its own tile before overwriting it
-        witness_scale_kernel<<<(n32 + 255) / 256, 256, 0, st>>>((const Fr *)poly_dev, q, n32, consts);
+        witness_scale_kernel<<<(n32 + 1023) / 1024, 256, 0, st>>>((const Fr *)poly_dev, q, n32, consts);
         PB_LAUNCHED(ctx);
         fr_scan_tile_sums_kernel<<<n_tiles, 256, 0, st>>>(q, n32, tiles);
         PB_LAUNCHED(ctx);

@@ -45,11 +45,14 @@ __device__ __forceinline__ void for_each_digit(const Fr &canon, uint32_t c, uint
     }
 }
 
+// blockIdx.y = scalar vector of a batched call (pre-doubled path): vector j reads scalars + j·stride and owns bucket set j.
 __global__ void __launch_bounds__(256) msm_count_kernel(const uint64_t *scalars, MsmCfg cfg, uint32_t *count) {
+    const uint32_t set = blockIdx.y << cfg.nb_log;
+    scalars += 4 * (size_t)blockIdx.y * cfg.scalar_stride;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cfg.n; i += (size_t)gridDim.x * blockDim.x) {
         Fr s = load_fr(scalars, i).from_mont();
         for_each_digit(s, cfg.c, cfg.W, [&](uint32_t w, uint32_t mag, uint32_t) {
-            atomicAdd(&count[(cfg.pre_stride ? 0u : (w << cfg.nb_log)) + mag - 1], 1u);
+            atomicAdd(&count[(cfg.pre_stride ? set : (w << cfg.nb_log)) + mag - 1], 1u);
         });
     }
 }
@@ -62,10 +65,12 @@ __global__ void __launch_bounds__(256) msm_count_kernel(const uint64_t *scalars,
 // in-flight-entries × 8 B ≈ 465 MB ≫ L2 and DRAM traffic triples — 74 ms instead of 42 ms — so it was dropped.)
 __global__ void __launch_bounds__(256) msm_scatter_kernel(const uint64_t *scalars, MsmCfg cfg, uint32_t *cursor, uint2 *entries,
                                                           uint32_t shift) {
+    const uint32_t set = blockIdx.y << cfg.nb_log;
+    scalars += 4 * (size_t)blockIdx.y * cfg.scalar_stride;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < cfg.n; i += (size_t)gridDim.x * blockDim.x) {
         Fr s = load_fr(scalars, i).from_mont();
         for_each_digit(s, cfg.c, cfg.W, [&](uint32_t w, uint32_t mag, uint32_t sign) {
-            const uint32_t gb = (cfg.pre_stride ? 0u : (w << cfg.nb_log)) + mag - 1;
+            const uint32_t gb = (cfg.pre_stride ? set : (w << cfg.nb_log)) + mag - 1;
             const uint32_t pos = atomicAdd(&cursor[gb >> shift], 1u);
             entries[pos] = make_uint2(gb, (uint32_t)(w * cfg.pre_stride + i) | (sign << 31));
         });
@@ -234,19 +239,25 @@ int msm_module_init(pb200_ctx *) { return 0; }
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // One piece (n < 2^27) of an MSM; bases / scalars on the device.
+// batch > 1 (pre-doubled path only): `batch` scalar vectors, `scalar_stride` scalars apart, against the same bases;
+// result_dev then receives `batch` records of 36 words.
 static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scalars, uint32_t n, int first, int last,
-                     G1Xyzz *running_total, uint32_t *result_dev, uint32_t pre_c, uint32_t pre_stride) {
+                     G1Xyzz *running_total, uint32_t *result_dev, uint32_t pre_c, uint32_t pre_stride, uint32_t batch = 1,
+                     uint32_t scalar_stride = 0) {
+    PB_ARG(ctx, batch >= 1 && (batch == 1 || (pre_stride && first && last)));
     MsmCfg cfg;
+    cfg.batch = batch;
+    cfg.scalar_stride = scalar_stride;
     cfg.n = n;
     cfg.c = pre_stride ? pre_c : choose_window(n);
     cfg.W = (256 + cfg.c - 1) / cfg.c;
     cfg.nb_log = cfg.c - 1;
     cfg.pre_stride = pre_stride;
-    const uint64_t m0 = (uint64_t)n * cfg.W;  // upper bound on entries
+    const uint64_t m0 = (uint64_t)n * cfg.W * batch;  // upper bound on entries
     PB_ARG(ctx, m0 < (1ull << 32));
     cfg.L1 = std::min<uint32_t>(128, std::max<uint32_t>(8, floor_pow2(m0 / 262144 + 1)));
     cfg.L2 = 16;
-    const uint32_t n_win = pre_stride ? 1u : cfg.W;   // bucket sets (windows to reduce / combine)
+    const uint32_t n_win = pre_stride ? batch : cfg.W;   // bucket sets (windows to reduce / combine)
     const uint32_t TB = n_win << cfg.nb_log;          // total buckets
     {   // chunk size for the bucket reduction: aim for ≥ 64 Ki chunk threads, 8 ≤ K ≤ 256
         uint32_t k_log = 3;
@@ -305,7 +316,7 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     PbTimer t_sort(ctx, "msm.sort");
     PB_CUDA(ctx, cudaMemsetAsync(count, 0, (size_t)TB * 4, st));
     const uint32_t sgrid = std::min<uint32_t>((n + 255) / 256, ctx->sm_count * 16);
-    msm_count_kernel<<<sgrid, 256, 0, st>>>(scalars, cfg, count);
+    msm_count_kernel<<<dim3(sgrid, batch), 256, 0, st>>>(scalars, cfg, count);
     PB_LAUNCHED(ctx);
     scan_block_sums_kernel<<<n_scan_blocks, kScanThreads, 0, st>>>(count, TB, bsum);
     PB_LAUNCHED(ctx);
@@ -316,11 +327,11 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     if (coarse_shift) {
         msm_coarse_init_kernel<<<(n_coarse + 255) / 256, 256, 0, st>>>(cursor, coarse, n_coarse, coarse_shift);
         PB_LAUNCHED(ctx);
-        msm_scatter_kernel<<<sgrid, 256, 0, st>>>(scalars, cfg, coarse, grouped, coarse_shift);
+        msm_scatter_kernel<<<dim3(sgrid, batch), 256, 0, st>>>(scalars, cfg, coarse, grouped, coarse_shift);
         PB_LAUNCHED(ctx);
         msm_fine_scatter_kernel<<<(uint32_t)((m0 + 255) / 256), 256, 0, st>>>(grouped, meta + 0, cursor, entries);
     } else {
-        msm_scatter_kernel<<<sgrid, 256, 0, st>>>(scalars, cfg, cursor, entries, 0);
+        msm_scatter_kernel<<<dim3(sgrid, batch), 256, 0, st>>>(scalars, cfg, cursor, entries, 0);
     }
     PB_LAUNCHED(ctx);
     t_sort.stop();
@@ -354,7 +365,8 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     } else {
         PB_TRY(tail_sum(ctx, n_win, 1, chunks, chunks_per_window, wsum));
     }
-    PB_TRY(tail_combine(ctx, wsum, rcfg, running_total, first, last, result_dev));
+    if (batch > 1) PB_TRY(tail_batch_results(ctx, wsum, batch, result_dev));
+    else PB_TRY(tail_combine(ctx, wsum, rcfg, running_total, first, last, result_dev));
     t_red.stop();
     if (ctx->profile) {
         PB_CUDA(ctx, cudaStreamSynchronize(st));
@@ -366,7 +378,36 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     return 0;
 }
 
-static int msm_run(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_dev, size_t n, uint64_t *out_host) {
+static int msm_run(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_dev, size_t n, uint64_t *out_host,
+                   uint32_t batch = 1, size_t scalar_stride = 0) {
+    if (batch > 1) {
+        // one pass over the shared bases when the pre-doubled copies are usable, otherwise one MSM after the other
+        const bool pre_ok = srs != nullptr && srs->pre != nullptr && n * 16 >= srs->n && (uint64_t)srs->W_pre * srs->n < (1ull << 31) &&
+                            (uint64_t)n * srs->W_pre * batch < (1ull << 32) && n <= ((size_t)1 << 26) && n > 0;
+        if (!pre_ok) {
+            for (uint32_t j = 0; j < batch; j++) PB_TRY(msm_run(ctx, srs, offset, scalars_dev + 4 * j * scalar_stride, n, out_host + 18 * j));
+            return 0;
+        }
+        PB_ARG(ctx, offset <= srs->n && n <= srs->n - offset && scalars_dev != nullptr && batch <= 64);
+        PB_CUDA(ctx, cudaSetDevice(ctx->device));
+        const G1Affine *bases = reinterpret_cast<const G1Affine *>(srs->pre) + offset;
+        void *small = nullptr;
+        PB_CUDA(ctx, cudaMallocAsync(&small, (size_t)batch * 36 * 4, ctx->stream));
+        PbTimer t_total(ctx, "msm.total");
+        int rc = msm_piece(ctx, bases, scalars_dev, (uint32_t)n, 1, 1, nullptr, (uint32_t *)small, srs->c_pre, (uint32_t)srs->n, batch,
+                           (uint32_t)scalar_stride);
+        t_total.stop();
+        cudaError_t e = cudaSuccess;
+        if (rc == 0) e = cudaMemcpyAsync(ctx->pinned, small, (size_t)batch * 36 * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
+        cudaFreeAsync(small, ctx->stream);
+        if (rc) return rc;
+        if (e != cudaSuccess || e2 != cudaSuccess)
+            return pb_fail(ctx, PB200_ERR_CUDA, "batched msm", cudaGetErrorString(e != cudaSuccess ? e : e2), __FILE__, __LINE__);
+        t_total.collect();
+        memcpy(out_host, ctx->pinned, (size_t)batch * 36 * 4);
+        return 0;
+    }
     // identity for the empty sum
     if (n == 0) {
         memset(out_host, 0, 18 * 8);
@@ -479,6 +520,12 @@ extern "C" int pb200_msm_g1_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t off
     if (!ctx) return PB200_ERR_ARG;
     PB_ARG(ctx, out_xyz_mont != nullptr);
     return msm_run(ctx, srs, offset, scalars_mont_dev, n, out_xyz_mont);
+}
+extern "C" int pb200_msm_g1_batch_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_mont_dev, size_t n,
+                                      uint32_t batch, size_t scalar_stride, uint64_t *out_xyz_mont) {
+    if (!ctx || !out_xyz_mont) return PB200_ERR_ARG;
+    PB_ARG(ctx, batch >= 1 && batch <= 64 && (batch == 1 || scalar_stride >= n) && scalar_stride < ((size_t)1 << 32));
+    return msm_run(ctx, srs, offset, scalars_mont_dev, n, out_xyz_mont, batch, scalar_stride);
 }
 extern "C" int pb200_msm_g1(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_mont_host, size_t n,
                             uint64_t out_xyz_mont[18]) {

@@ -16,6 +16,9 @@ struct MsmCfg {
     uint32_t K_log;   // log2 buckets per reduction chunk
     uint32_t pre_stride;  // 0, or the SRS length when pre-doubled copies are used: window w reads base w·stride + i
                           // and every window shares the bucket set of window 0
+    uint32_t batch;          // pre-doubled path only: number of scalar vectors summed over the same bases in one pass
+                             // (blockIdx.y of the count / scatter kernels); vector j owns bucket set j
+    uint32_t scalar_stride;  // distance between consecutive scalar vectors, in scalars
 };
 
 // ------------------------------------------------------------------------------------------ loads
@@ -69,6 +72,7 @@ int tail_reduce_chunks(pb200_ctx *ctx, uint32_t n_chunks, const G1Xyzz *buckets,
 int tail_sum(pb200_ctx *ctx, uint32_t groups, uint32_t parts, const G1Xyzz *in, uint32_t items_per_group, G1Xyzz *out);
 int tail_combine(pb200_ctx *ctx, const G1Xyzz *window_sums, MsmCfg cfg, G1Xyzz *running_total, int first_piece, int last_piece,
                  uint32_t *result);
+int tail_batch_results(pb200_ctx *ctx, const G1Xyzz *set_sums, uint32_t batch, uint32_t *results);
 int tail_g1_sum(pb200_ctx *ctx, const uint32_t *pts, uint32_t count, uint32_t *result);
 int tail_precompute(pb200_ctx *ctx, const G1Affine *bases, uint32_t n, uint32_t c, uint32_t W, G1Affine *pre);
 int tail_synthetic_bases(pb200_ctx *ctx, G1Affine *out, uint64_t n, uint64_t a, uint64_t d);

@@ -123,6 +123,12 @@ __global__ void msm_combine_kernel(const G1Xyzz *window_sums, MsmCfg cfg, G1Xyzz
     if (last_piece) write_projective(total, result);
 }
 
+// Batched MSM over pre-doubled bases: bucket set j already holds the whole sum of scalar vector j.
+__global__ void msm_batch_results_kernel(const G1Xyzz *set_sums, uint32_t batch, uint32_t *results) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < batch) write_projective(load_xyzz(set_sums + j), results + 36 * j);
+}
+
 // Σ of `count` projective (X:Y:Z) points given as 36-word records; one thread (count is a handful of ranks).
 __global__ void g1_sum_kernel(const uint32_t *pts, uint32_t count, uint32_t *result) {
     G1Xyzz total = G1Xyzz::identity();
@@ -210,6 +216,11 @@ int tail_sum(pb200_ctx *ctx, uint32_t groups, uint32_t parts, const G1Xyzz *in, 
 int tail_combine(pb200_ctx *ctx, const G1Xyzz *window_sums, MsmCfg cfg, G1Xyzz *running_total, int first_piece, int last_piece,
                  uint32_t *result) {
     msm_combine_kernel<<<1, 1, 0, ctx->stream>>>(window_sums, cfg, running_total, first_piece, last_piece, result);
+    PB_LAUNCHED(ctx);
+    return 0;
+}
+int tail_batch_results(pb200_ctx *ctx, const G1Xyzz *set_sums, uint32_t batch, uint32_t *results) {
+    msm_batch_results_kernel<<<1, 32, 0, ctx->stream>>>(set_sums, batch, results);
     PB_LAUNCHED(ctx);
     return 0;
 }

@@ -46,7 +46,7 @@ inline Fr to_dev(const HFr &h) {  // same memory image: 4 × u64 LE = 8 × u32 L
 __global__ void powers_kernel(Fr *out, uint32_t n, Fr c, Fr g) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    st_fr(out + i, c * g.pow_u64(i));
+    st_fr(out + i, c * g.pow_u32(i));
 }
 // dst[j] = j < n_src ? src[j] : 0 for `batch` vectors (dst stride n_dst, src stride n_src)
 __global__ void pad_copy_kernel(Fr *dst, const Fr *src, uint32_t n_src, uint32_t n_dst) {
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(256) poly_eval_partial_kernel(const EvalArgs A
         const uint32_t last = min(first + kEvalPerThread, len);
         acc = ld_fr(p + last - 1);
         for (uint32_t j = last - 1; j-- > first;) acc = acc * x + ld_fr(p + j);
-        acc = acc * x.pow_u64(first);
+        acc = acc * x.pow_u32(first);
     }
     acc = block_sum(acc, sm);
     if (threadIdx.x == 0) st_fr(A.partial + (size_t)job * A.tiles + blockIdx.x, acc);
@@ -390,7 +390,7 @@ void carve(pb200_prover_key *pk, void *base, size_t *total) {
     pk->t_poly = c.take<Fr>(N4);
     pk->lin_poly = c.take<Fr>(n);
     pk->agg = c.take<Fr>(n);
-    pk->wit = c.take<Fr>(n);
+    pk->wit = c.take<Fr>(2 * n);
     pk->num = c.take<Fr>(n);
     pk->den = c.take<Fr>(n);
     pk->small = c.take<Fr>(64 + 2 * scan_tiles(n) + kMaxJobs * eval_tiles(N4));
@@ -415,6 +415,15 @@ int commit_bytes(pb200_ctx *ctx, const pb200_srs *srs, const Fr *poly, size_t n,
     uint64_t xyz[18];
     PB_TRY(pb200_msm_g1_dev(ctx, srs, 0, (const uint64_t *)poly, n, xyz));
     hostf::g1_projective_to_bytes(xyz, out);
+    return 0;
+}
+
+// commit(`batch` polynomials of n coefficients, `stride` scalars apart) in one pass over the commit key
+int commit_bytes_batch(pb200_ctx *ctx, const pb200_srs *srs, const Fr *polys, size_t n, uint32_t batch, size_t stride, uint8_t *out) {
+    uint64_t xyz[18 * 16];
+    PB_ARG(ctx, batch <= 16);
+    PB_TRY(pb200_msm_g1_batch_dev(ctx, srs, 0, (const uint64_t *)polys, n, batch, stride, xyz));
+    for (uint32_t j = 0; j < batch; j++) hostf::g1_projective_to_bytes(xyz + 18 * j, out + 48 * j);
     return 0;
 }
 
@@ -588,7 +597,7 @@ extern "C" int pb200_preprocess(pb200_ctx *ctx, const pb200_srs *srs, const pb20
     }
     PK_CUDA(cudaMemcpyAsync(pk->sig_poly, pk->sig_evals, 4 * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     PK_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)pk->sig_poly, log_n, 4, 1, 0));
-    for (int c = 0; c < 4; c++) PK_TRY(commit_bytes(ctx, srs, pk->sig_poly + (size_t)c * n, n, vk + 48 * (kSel + c)));
+    PK_TRY(commit_bytes_batch(ctx, srs, pk->sig_poly, n, 4, n, vk + 48 * kSel));
     PK_TRY(coset_extend(ctx, pk->sig_4n, pk->sig_poly, (uint32_t)n, log_n + 2, 4));
     PK_CUDA(cudaStreamSynchronize(st));
 
@@ -635,10 +644,8 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
     PB_CUDA(ctx, cudaMemcpyAsync(pk->w_poly, pk->w_evals, 4 * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     PB_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)pk->w_poly, log_n, 4, 1, 0));
     const char *const w_label[4] = {"w_l", "w_r", "w_o", "w_4"};
-    for (int c = 0; c < 4; c++) {
-        PB_TRY(commit_bytes(ctx, srs, pk->w_poly + (size_t)c * n, n, P + 48 * c));
-        tr.append_commitment(w_label[c], P + 48 * c);
-    }
+    PB_TRY(commit_bytes_batch(ctx, srs, pk->w_poly, n, 4, n, P));
+    for (int c = 0; c < 4; c++) tr.append_commitment(w_label[c], P + 48 * c);
     clk.lap("prove.round1");
 
     // ---- round 2: permutation polynomial ------------------------------------------------------------------------------
@@ -716,10 +723,8 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
     }
     PB_TRY(pb200_ntt_dev(ctx, (uint64_t *)pk->t_poly, log_n + 2, 1, 1));
     const char *const t_label[4] = {"t_1", "t_2", "t_3", "t_4"};
-    for (int k = 0; k < 4; k++) {
-        PB_TRY(commit_bytes(ctx, srs, pk->t_poly + (size_t)k * n, n, P + 48 * (5 + k)));
-        tr.append_commitment(t_label[k], P + 48 * (5 + k));
-    }
+    PB_TRY(commit_bytes_batch(ctx, srs, pk->t_poly, n, 4, n, P + 48 * 5));
+    for (int k = 0; k < 4; k++) tr.append_commitment(t_label[k], P + 48 * (5 + k));
     clk.lap("prove.round3");
 
     // ---- round 4: evaluations and the linearisation polynomial -------------------------------------------------------------
@@ -875,9 +880,10 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
         PB_LAUNCHED(ctx);
         uint64_t point[4], unused[4];
         (which == 0 ? z : zw).store(point);
-        PB_TRY(pb200_kzg_witness_dev(ctx, (const uint64_t *)pk->agg, n, point, (uint64_t *)pk->wit, unused));
-        PB_TRY(commit_bytes(ctx, srs, pk->wit, n, P + 48 * (9 + which)));
+        PB_TRY(pb200_kzg_witness_dev(ctx, (const uint64_t *)pk->agg, n, point, (uint64_t *)(pk->wit + (size_t)which * n), unused));
     }
+    // the second challenge is squeezed before either witness is committed, so both commitments are one batched MSM
+    PB_TRY(commit_bytes_batch(ctx, srs, pk->wit, n, 2, n, P + 48 * 9));
     clk.lap("prove.round5");
     return 0;
 }

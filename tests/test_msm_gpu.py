@@ -250,3 +250,37 @@ def test_two_level_scatter_path(ctx, oracle, monkeypatch):
     finally:
         ctx.srs_free(srs)
         ctx.srs_free(srs_pre)
+
+
+@pytest.mark.parametrize("n,batch,pre", [(1 << 12, 4, True), (1000, 3, True), (1 << 14, 2, True), (1 << 12, 4, False), (77, 5, True)])
+def test_batched_msm_matches_single_calls(ctx, oracle, n, batch, pre):
+    """pb200_msm_g1_batch_dev: several scalar vectors over the same bases in one pass (own bucket set each) — equal,
+    vector by vector, to separate calls and to the oracle; adversarial vectors (all zero, all one) ride along."""
+    pts = oracle.synthetic_bases(n)
+    srs = ctx.srs_upload(pts)
+    if pre:
+        ctx.srs_precompute(srs)
+    stride = n + 5
+    vecs = []
+    for j in range(batch):
+        if j == 1:
+            vals = [0] * n
+        elif j == 2:
+            vals = [1] * n
+        else:
+            vals = model.random_fr(0xBA7C0 + j, n)
+        vecs.append(oracle.fr_to_mont(oracle.ints_to_limbs(vals, 4)))
+    buf = np.zeros((batch * stride, 4), np.uint64)
+    for j, v in enumerate(vecs):
+        buf[j * stride:j * stride + n] = v
+    dev = ctx.malloc(buf.nbytes)
+    ctx.h2d(dev, buf)
+    try:
+        got = ctx.msm_batch_dev(srs, dev, n, batch, stride)
+        for j, v in enumerate(vecs):
+            want = aff(oracle, oracle.msm_variable_base(pts, v, threads=8))
+            assert aff(oracle, got[j]) == want, j
+            assert aff(oracle, ctx.msm(srs, v)) == want, j
+    finally:
+        ctx.free(dev)
+        ctx.srs_free(srs)
