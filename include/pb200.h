@@ -138,6 +138,9 @@ PB200_API uint32_t pb200_msm_window_bits(size_t n);
 /* PublicParameters::setup: powers_of_g[i] = τ^i·G for i < n_points, generated on the device and resident (τ given
  * in Montgomery form, non-zero; the G2 side of the parameters belongs to the host verifier). */
 PB200_API int pb200_srs_generate(pb200_ctx *ctx, const uint64_t tau_mont[4], size_t n_points, pb200_srs **out);
+/* The slice powers_of_g[first .. first + n_points) of the same parameters: what one rank of a point-range-sharded
+ * prover holds. */
+PB200_API int pb200_srs_generate_range(pb200_ctx *ctx, const uint64_t tau_mont[4], size_t first, size_t n_points, pb200_srs **out);
 /* Device address of an SRS's packed affine points (n × 96 B), e.g. to serialise the CommitKey. */
 PB200_API const uint64_t *pb200_srs_dev_ptr(const pb200_srs *srs);
 /* CommitKey::compute_single_witness: p(z) and q(X) = (p(X) − p(z)) / (X − z) for a device-resident polynomial of
@@ -173,6 +176,24 @@ PB200_API int pb200_preprocess(pb200_ctx *ctx, const pb200_srs *srs, const pb200
 PB200_API void pb200_prover_key_free(pb200_ctx *ctx, pb200_prover_key *pk);
 PB200_API size_t pb200_prover_key_size(const pb200_prover_key *pk);  /* padded circuit size n */
 PB200_API size_t pb200_prover_key_bytes(const pb200_prover_key *pk); /* device memory held */
+/* Point-range-sharded proving over `world` GPUs, one process per GPU (BASELINE.json configs[4]): every
+ * commitment of preprocessing and of the five rounds is an MSM over this rank's slice of the commit key
+ * (powers_of_g[rank·n/world .. (rank+1)·n/world), see pb200_srs_generate_range) against the matching coefficient slice;
+ * the `world` partial sums (144 bytes each) are exchanged through `allgather` — the host's NCCL / gloo all-gather —
+ * and added, so every rank derives the same transcript challenges and returns the same proof.  NTTs and pointwise
+ * kernels run replicated on every rank (they are ~15 % of a single-GPU prove).  The callback receives `bytes` bytes in
+ * `send` and must fill `recv` with world × bytes, rank-major; non-zero return aborts the call. */
+typedef int (*pb200_allgather_fn)(void *user, const void *send, void *recv, size_t bytes);
+typedef struct pb200_shard {
+    uint32_t rank, world;
+    pb200_allgather_fn allgather;
+    void *user;
+} pb200_shard;
+/* As pb200_preprocess, with `srs` holding this rank's slice.  The shard description is kept in the key: pb200_prove on a
+ * sharded key must be given the same slice and is collective over all ranks. */
+PB200_API int pb200_preprocess_sharded(pb200_ctx *ctx, const pb200_srs *srs_slice, const pb200_circuit *circuit,
+                                       const uint8_t *transcript_label, size_t label_len, const pb200_shard *shard,
+                                       pb200_prover_key **out, uint8_t vk_commitments[15 * 48]);
 /* Prover::prove_with_preprocessed + Proof::to_bytes: the witness is the value of every variable (n_vars Montgomery
  * scalars, host), the public inputs a sparse (gate index, value) list.  Rounds 1-5 run on the device with the
  * polynomials resident between rounds; the host hashes the transcript.  proof_out: 11 compressed G1 + 16 scalars.

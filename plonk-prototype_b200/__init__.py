@@ -4,4 +4,4 @@ from ._native import Context, Pb200Error, LIB_PATH, EXPORTS  # noqa: F401
 from .domain import EvaluationDomain, InvalidEvalDomainSize, default_context  # noqa: F401
 from .msm import msm_variable_base, CommitKey, g1_to_bytes  # noqa: F401
 from .dist_ntt import DistributedDomain, ShardSpec, GpuBackend, PeerBuffers  # noqa: F401
-from .prover import StandardComposer, Prover, PublicParameters, scalars_to_mont  # noqa: F401
+from .prover import StandardComposer, Prover, PublicParameters, ShardedParameters, torch_allgather, scalars_to_mont  # noqa: F401

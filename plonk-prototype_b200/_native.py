@@ -19,8 +19,8 @@ EXPORTS = [
     "pb200_ipc_export", "pb200_ipc_open", "pb200_ipc_close", "pb200_block_transpose_dev",
     "pb200_srs_upload", "pb200_srs_wrap_dev", "pb200_srs_precompute", "pb200_srs_free", "pb200_srs_len",
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_batch_dev", "pb200_g1_sum", "pb200_msm_window_bits",
-    "pb200_srs_generate", "pb200_srs_dev_ptr", "pb200_kzg_witness_dev", "pb200_fr_horner_step_dev",
-    "pb200_preprocess", "pb200_prover_key_free", "pb200_prover_key_size", "pb200_prover_key_bytes", "pb200_prove",
+    "pb200_srs_generate", "pb200_srs_generate_range", "pb200_srs_dev_ptr", "pb200_kzg_witness_dev", "pb200_fr_horner_step_dev",
+    "pb200_preprocess", "pb200_preprocess_sharded", "pb200_prover_key_free", "pb200_prover_key_size", "pb200_prover_key_bytes", "pb200_prove",
     "pb200_transcript_selftest",
     "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_launch_count",
     "pb200_imad_peak",
@@ -29,6 +29,14 @@ EXPORTS = [
 
 class Pb200Error(RuntimeError):
     pass
+
+
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+
+class Shard(ctypes.Structure):
+    """`pb200_shard` (include/pb200.h)."""
+    _fields_ = [("rank", ctypes.c_uint32), ("world", ctypes.c_uint32), ("allgather", ALLGATHER_FN), ("user", ctypes.c_void_p)]
 
 
 class Circuit(ctypes.Structure):
@@ -87,6 +95,9 @@ def lib():
         L.pb200_kzg_witness_dev.argtypes = [vp, u64p, ctypes.c_size_t, u64p, u64p, u64p]
         L.pb200_fr_horner_step_dev.argtypes = [vp, u64p, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]
         L.pb200_preprocess.argtypes = [vp, vp, ctypes.POINTER(Circuit), ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), vp]
+        L.pb200_preprocess_sharded.argtypes = [vp, vp, ctypes.POINTER(Circuit), ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(Shard),
+                                               ctypes.POINTER(vp), vp]
+        L.pb200_srs_generate_range.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(vp)]
         L.pb200_prover_key_free.argtypes = [vp, vp]
         L.pb200_prover_key_free.restype = None
         L.pb200_prover_key_size.argtypes = [vp]
@@ -247,6 +258,12 @@ class Context:
         self._check(lib().pb200_srs_generate(self._h, _ptr(tau), n, ctypes.byref(h)))
         return h
 
+    def srs_generate_range(self, tau_mont, first, n):
+        tau = np.ascontiguousarray(tau_mont, dtype=np.uint64).reshape(4)
+        h = ctypes.c_void_p()
+        self._check(lib().pb200_srs_generate_range(self._h, _ptr(tau), first, n, ctypes.byref(h)))
+        return h
+
     def srs_dev_ptr(self, srs):
         return lib().pb200_srs_dev_ptr(srs)
 
@@ -261,8 +278,10 @@ class Context:
         self._check(lib().pb200_fr_horner_step_dev(self._h, ctypes.c_void_p(acc_dev), n_acc, ctypes.c_void_p(poly_dev), n_poly, _ptr(c)))
 
     # -- PLONK prover rounds
-    def preprocess(self, srs, selectors, wires, n_vars, label):
-        """selectors: 11 (n_gates, 4) uint64 arrays or None; wires: 4 uint32 arrays.  Returns (key handle, 15×48 vk bytes)."""
+    def preprocess(self, srs, selectors, wires, n_vars, label, shard=None):
+        """selectors: 11 (n_gates, 4) uint64 arrays or None; wires: 4 uint32 arrays.  Returns (key handle, 15×48 vk bytes).
+        shard = (rank, world, allgather) makes the key point-range-sharded: `srs` is this rank's slice and
+        allgather(send: bytes) -> bytes of world × len(send), rank-major, is the host's collective."""
         keep = []
         c = Circuit()
         c.n_gates = len(wires[0])
@@ -282,7 +301,30 @@ class Context:
             c.wires[k] = a.ctypes.data
         h = ctypes.c_void_p()
         vk = np.zeros(15 * 48, np.uint8)
-        self._check(lib().pb200_preprocess(self._h, srs, ctypes.byref(c), bytes(label), len(label), ctypes.byref(h), _ptr(vk)))
+        if shard is None:
+            self._check(lib().pb200_preprocess(self._h, srs, ctypes.byref(c), bytes(label), len(label), ctypes.byref(h), _ptr(vk)))
+            return h, vk.tobytes()
+        rank, world, gather = shard
+
+        def trampoline(_user, send, recv, nbytes):
+            try:
+                out = gather(ctypes.string_at(send, nbytes))
+                if len(out) != world * nbytes:
+                    return 1
+                ctypes.memmove(recv, out, len(out))
+                return 0
+            except Exception:  # never let an exception cross the C ABI
+                import traceback
+                traceback.print_exc()
+                return 2
+
+        cb = ALLGATHER_FN(trampoline)
+        sh = Shard(rank, world, cb, None)
+        self._check(lib().pb200_preprocess_sharded(self._h, srs, ctypes.byref(c), bytes(label), len(label), ctypes.byref(sh),
+                                                   ctypes.byref(h), _ptr(vk)))
+        if not hasattr(self, "_keepalive"):
+            self._keepalive = {}
+        self._keepalive[h.value] = cb  # the key holds the function pointer for every later pb200_prove
         return h, vk.tobytes()
 
     def prover_key_free(self, pk):

@@ -53,10 +53,11 @@ __global__ void __launch_bounds__(128) srs_table_kernel(const G1Affine *bases32,
     store_fp2(reinterpret_cast<uint4 *>(table + t), a.x, a.y);
 }
 // out[i] = τ^i·G: τ^i by square-and-multiply, then one table lookup and mixed addition per scalar byte.
-__global__ void __launch_bounds__(128) srs_powers_kernel(const G1Affine *__restrict__ table, const Fr *tau, uint32_t n, G1Affine *out) {
+__global__ void __launch_bounds__(128) srs_powers_kernel(const G1Affine *__restrict__ table, const Fr *tau, uint32_t first, uint32_t n,
+                                                         G1Affine *out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const Fr s = ld_fr(tau).pow_u32(i).from_mont();
+    const Fr s = ld_fr(tau).pow_u32(first + i).from_mont();
     G1Xyzz acc = G1Xyzz::identity();
     for (uint32_t w = 0; w < 32; w++) {
         const uint32_t d = (s.l[w >> 2] >> (8 * (w & 3))) & 0xff;
@@ -177,8 +178,11 @@ __global__ void witness_shift_kernel(const Fr *a, uint32_t n, Fr *q, Fr *eval) {
 }  // namespace
 
 extern "C" int pb200_srs_generate(pb200_ctx *ctx, const uint64_t tau_mont[4], size_t n_points, pb200_srs **out) {
+    return pb200_srs_generate_range(ctx, tau_mont, 0, n_points, out);
+}
+extern "C" int pb200_srs_generate_range(pb200_ctx *ctx, const uint64_t tau_mont[4], size_t first, size_t n_points, pb200_srs **out) {
     if (!ctx) return PB200_ERR_ARG;
-    PB_ARG(ctx, tau_mont != nullptr && out != nullptr && n_points >= 1 && n_points < ((size_t)1 << 31));
+    PB_ARG(ctx, tau_mont != nullptr && out != nullptr && n_points >= 1 && first + n_points < ((size_t)1 << 31));
     PB_ARG(ctx, (tau_mont[0] | tau_mont[1] | tau_mont[2] | tau_mont[3]) != 0);
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     void *table = nullptr, *tau = nullptr, *pts = nullptr;
@@ -192,7 +196,7 @@ extern "C" int pb200_srs_generate(pb200_ctx *ctx, const uint64_t tau_mont[4], si
         srs_table_kernel<<<(32 * 255 + 127) / 128, 128, 0, ctx->stream>>>(bases32, (G1Affine *)table);
         ctx->launches++;
         srs_powers_kernel<<<(uint32_t)((n_points + 127) / 128), 128, 0, ctx->stream>>>((const G1Affine *)table, (const Fr *)tau,
-                                                                                     (uint32_t)n_points, (G1Affine *)pts);
+                                                                                     (uint32_t)first, (uint32_t)n_points, (G1Affine *)pts);
         ctx->launches += 2;
         e = cudaGetLastError();
     }

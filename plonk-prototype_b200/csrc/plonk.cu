@@ -348,6 +348,9 @@ struct pb200_prover_key {
     HFr omega, omega4;
     uint8_t vk_bytes[15 * 48];
     merlin::Transcript *seeded = nullptr;
+    // point-range sharding of the commitments (world = 1: none)
+    pb200_shard shard = {0, 1, nullptr, nullptr};
+    size_t slice_lo = 0, slice_n = 0;  // this rank's coefficient range [slice_lo, slice_lo + slice_n)
 };
 
 namespace {
@@ -410,21 +413,32 @@ int launch_scan(pb200_ctx *ctx, pb200_prover_key *pk, Fr *a, uint32_t n, bool re
     return 0;
 }
 
-// commit(poly of n coefficients) → 48 compressed bytes
-int commit_bytes(pb200_ctx *ctx, const pb200_srs *srs, const Fr *poly, size_t n, uint8_t out[48]) {
-    uint64_t xyz[18];
-    PB_TRY(pb200_msm_g1_dev(ctx, srs, 0, (const uint64_t *)poly, n, xyz));
-    hostf::g1_projective_to_bytes(xyz, out);
-    return 0;
-}
-
-// commit(`batch` polynomials of n coefficients, `stride` scalars apart) in one pass over the commit key
-int commit_bytes_batch(pb200_ctx *ctx, const pb200_srs *srs, const Fr *polys, size_t n, uint32_t batch, size_t stride, uint8_t *out) {
+// commit(`batch` polynomials of n coefficients, `stride` scalars apart) → 48 compressed bytes each.  Single GPU: one
+// batched pass over the commit key.  Sharded: the MSM runs over this rank's coefficient slice against its slice of
+// the key, the partial sums are all-gathered through the host's collective and added (pb200_g1_sum).
+int commit_bytes_batch(pb200_ctx *ctx, const pb200_srs *srs, const pb200_prover_key *pk, const Fr *polys, size_t n, uint32_t batch,
+                       size_t stride, uint8_t *out) {
     uint64_t xyz[18 * 16];
     PB_ARG(ctx, batch <= 16);
-    PB_TRY(pb200_msm_g1_batch_dev(ctx, srs, 0, (const uint64_t *)polys, n, batch, stride, xyz));
+    if (pk->shard.world <= 1) {
+        PB_TRY(pb200_msm_g1_batch_dev(ctx, srs, 0, (const uint64_t *)polys, n, batch, stride, xyz));
+    } else {
+        PB_ARG(ctx, n == pk->n);
+        PB_TRY(pb200_msm_g1_batch_dev(ctx, srs, 0, (const uint64_t *)(polys + pk->slice_lo), pk->slice_n, batch, stride, xyz));
+        const uint32_t world = pk->shard.world;
+        std::vector<uint64_t> all((size_t)world * batch * 18), one((size_t)world * 18);
+        if (pk->shard.allgather(pk->shard.user, xyz, all.data(), (size_t)batch * 144) != 0)
+            return pb_fail(ctx, PB200_ERR_ARG, "sharded commit", "the all-gather callback failed", __FILE__, __LINE__);
+        for (uint32_t j = 0; j < batch; j++) {
+            for (uint32_t r = 0; r < world; r++) memcpy(&one[(size_t)r * 18], &all[((size_t)r * batch + j) * 18], 144);
+            PB_TRY(pb200_g1_sum(ctx, one.data(), world, xyz + 18 * j));
+        }
+    }
     for (uint32_t j = 0; j < batch; j++) hostf::g1_projective_to_bytes(xyz + 18 * j, out + 48 * j);
     return 0;
+}
+int commit_bytes(pb200_ctx *ctx, const pb200_srs *srs, const pb200_prover_key *pk, const Fr *poly, size_t n, uint8_t out[48]) {
+    return commit_bytes_batch(ctx, srs, pk, poly, n, 1, n, out);
 }
 
 int coset_extend(pb200_ctx *ctx, Fr *dst, const Fr *src, uint32_t n, uint32_t log_n4, uint32_t batch) {
@@ -462,7 +476,14 @@ extern "C" size_t pb200_prover_key_bytes(const pb200_prover_key *pk) { return pk
 
 extern "C" int pb200_preprocess(pb200_ctx *ctx, const pb200_srs *srs, const pb200_circuit *circuit, const uint8_t *transcript_label,
                                 size_t label_len, pb200_prover_key **out, uint8_t vk_commitments[15 * 48]) {
+    return pb200_preprocess_sharded(ctx, srs, circuit, transcript_label, label_len, nullptr, out, vk_commitments);
+}
+extern "C" int pb200_preprocess_sharded(pb200_ctx *ctx, const pb200_srs *srs, const pb200_circuit *circuit,
+                                        const uint8_t *transcript_label, size_t label_len, const pb200_shard *shard,
+                                        pb200_prover_key **out, uint8_t vk_commitments[15 * 48]) {
     if (!ctx) return PB200_ERR_ARG;
+    const uint32_t world = shard ? shard->world : 1;
+    PB_ARG(ctx, world >= 1 && (world & (world - 1)) == 0 && (world == 1 || (shard->allgather != nullptr && shard->rank < world)));
     PB_ARG(ctx, srs != nullptr && circuit != nullptr && out != nullptr && (transcript_label != nullptr || label_len == 0));
     PB_ARG(ctx, circuit->n_gates >= 1 && circuit->n_vars >= 1 && circuit->n_vars < ((size_t)1 << 32));
     for (int c = 0; c < 4; c++) PB_ARG(ctx, circuit->wires[c] != nullptr);
@@ -470,10 +491,13 @@ extern "C" int pb200_preprocess(pb200_ctx *ctx, const pb200_srs *srs, const pb20
     PB_TRY(pb200_domain_log_size(circuit->n_gates, &log_n));
     PB_ARG(ctx, log_n <= 26);  // 4n domain (2^28 scalars = 8 GiB per vector) and the 2-bit column tag of the permutation map
     const size_t n = (size_t)1 << log_n, N4 = 4 * n, ng = circuit->n_gates;
-    PB_ARG(ctx, pb200_srs_len(srs) >= n);
+    PB_ARG(ctx, world <= n && pb200_srs_len(srs) >= n / world);
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
 
     pb200_prover_key *pk = new pb200_prover_key();
+    if (world > 1) pk->shard = *shard;
+    pk->slice_n = n / world;
+    pk->slice_lo = (size_t)pk->shard.rank * pk->slice_n;
     pk->log_n = log_n;
     pk->n = n;
     pk->n_gates = ng;
@@ -592,12 +616,12 @@ extern "C" int pb200_preprocess(pb200_ctx *ctx, const pb200_srs *srs, const pb20
         PK_CUDA(cudaMemsetAsync(pk->q_poly[s], 0, n * sizeof(Fr), st));
         PK_CUDA(cudaMemcpyAsync(pk->q_poly[s], circuit->selectors[s], ng * sizeof(Fr), cudaMemcpyHostToDevice, st));
         PK_TRY(pb200_ntt_dev(ctx, (uint64_t *)pk->q_poly[s], log_n, 1, 0));
-        PK_TRY(commit_bytes(ctx, srs, pk->q_poly[s], n, dst));
+        PK_TRY(commit_bytes(ctx, srs, pk, pk->q_poly[s], n, dst));
         PK_TRY(coset_extend(ctx, pk->q_4n[s], pk->q_poly[s], (uint32_t)n, log_n + 2, 1));
     }
     PK_CUDA(cudaMemcpyAsync(pk->sig_poly, pk->sig_evals, 4 * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     PK_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)pk->sig_poly, log_n, 4, 1, 0));
-    PK_TRY(commit_bytes_batch(ctx, srs, pk->sig_poly, n, 4, n, vk + 48 * kSel));
+    PK_TRY(commit_bytes_batch(ctx, srs, pk, pk->sig_poly, n, 4, n, vk + 48 * kSel));
     PK_TRY(coset_extend(ctx, pk->sig_4n, pk->sig_poly, (uint32_t)n, log_n + 2, 4));
     PK_CUDA(cudaStreamSynchronize(st));
 
@@ -620,7 +644,7 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
     if (!ctx) return PB200_ERR_ARG;
     PB_ARG(ctx, srs != nullptr && pk != nullptr && values_mont != nullptr && proof_out != nullptr);
     PB_ARG(ctx, n_pi == 0 || (pi_gate != nullptr && pi_mont != nullptr));
-    PB_ARG(ctx, pb200_srs_len(srs) >= pk->n);
+    PB_ARG(ctx, pb200_srs_len(srs) >= pk->slice_n);
     for (size_t j = 0; j < n_pi; j++) PB_ARG(ctx, pi_gate[j] < pk->n);
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -644,7 +668,7 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
     PB_CUDA(ctx, cudaMemcpyAsync(pk->w_poly, pk->w_evals, 4 * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     PB_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)pk->w_poly, log_n, 4, 1, 0));
     const char *const w_label[4] = {"w_l", "w_r", "w_o", "w_4"};
-    PB_TRY(commit_bytes_batch(ctx, srs, pk->w_poly, n, 4, n, P));
+    PB_TRY(commit_bytes_batch(ctx, srs, pk, pk->w_poly, n, 4, n, P));
     for (int c = 0; c < 4; c++) tr.append_commitment(w_label[c], P + 48 * c);
     clk.lap("prove.round1");
 
@@ -662,7 +686,7 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
     perm_finish_kernel<<<cdiv(n, 256), 256, 0, st>>>(pk->num, pk->den, scal + 2, n32, pk->z_poly);
     PB_LAUNCHED(ctx);
     PB_TRY(pb200_ntt_dev(ctx, (uint64_t *)pk->z_poly, log_n, 1, 0));
-    PB_TRY(commit_bytes(ctx, srs, pk->z_poly, n, P + 48 * 4));
+    PB_TRY(commit_bytes(ctx, srs, pk, pk->z_poly, n, P + 48 * 4));
     tr.append_commitment("z", P + 48 * 4);
     clk.lap("prove.round2");
 
@@ -723,7 +747,7 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
     }
     PB_TRY(pb200_ntt_dev(ctx, (uint64_t *)pk->t_poly, log_n + 2, 1, 1));
     const char *const t_label[4] = {"t_1", "t_2", "t_3", "t_4"};
-    PB_TRY(commit_bytes_batch(ctx, srs, pk->t_poly, n, 4, n, P + 48 * 5));
+    PB_TRY(commit_bytes_batch(ctx, srs, pk, pk->t_poly, n, 4, n, P + 48 * 5));
     for (int k = 0; k < 4; k++) tr.append_commitment(t_label[k], P + 48 * (5 + k));
     clk.lap("prove.round3");
 
@@ -883,7 +907,7 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
         PB_TRY(pb200_kzg_witness_dev(ctx, (const uint64_t *)pk->agg, n, point, (uint64_t *)(pk->wit + (size_t)which * n), unused));
     }
     // the second challenge is squeezed before either witness is committed, so both commitments are one batched MSM
-    PB_TRY(commit_bytes_batch(ctx, srs, pk->wit, n, 2, n, P + 48 * 9));
+    PB_TRY(commit_bytes_batch(ctx, srs, pk, pk->wit, n, 2, n, P + 48 * 9));
     clk.lap("prove.round5");
     return 0;
 }

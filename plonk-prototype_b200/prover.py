@@ -134,6 +134,41 @@ class PublicParameters:
             self.srs = None
 
 
+def torch_allgather(dist, device=None):
+    """The all-gather a sharded key calls between an MSM and the transcript: bytes in → world × bytes out, rank-major.
+    `dist` is torch.distributed with an initialised process group (NCCL over NVLink on the GPU box — `device` is then
+    this rank's cuda device — or gloo in the CPU tests)."""
+    import torch
+
+    def gather(send):
+        t = torch.frombuffer(bytearray(send), dtype=torch.uint8)
+        if device is not None:
+            t = t.to(device)
+        out = torch.empty(dist.get_world_size() * t.numel(), dtype=torch.uint8, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy().tobytes()
+
+    return gather
+
+
+class ShardedParameters:
+    """This rank's slice powers_of_g[rank·n/world .. (rank+1)·n/world) of `PublicParameters::setup(n − 1)`."""
+
+    def __init__(self, n_points, tau, rank, world, ctx=None, precompute=True):
+        assert n_points % world == 0
+        self.ctx = ctx or default_context()
+        self.n_points, self.rank, self.world = n_points, rank, world
+        per = n_points // world
+        self.srs = self.ctx.srs_generate_range(scalars_to_mont([tau]), rank * per, per)
+        if precompute and per <= (1 << 22):
+            self.ctx.srs_precompute(self.srs)
+
+    def close(self):
+        if self.srs is not None:
+            self.ctx.srs_free(self.srs)
+            self.srs = None
+
+
 class Prover:
     """`Prover::new(label)`, `.mut_cs()`, `.preprocess(&ck)`, `.prove(&ck)`."""
 
