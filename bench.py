@@ -349,6 +349,10 @@ def run_ours(args, rank, world, local_rank):
         sharded = bench_ntt_sharded(ctx, dist, rank, world, args)
         if rank == 0:
             extra["ntt_sharded"] = sharded
+        if not args.skip_prove:
+            ps = bench_prove_sharded(ctx, dist, rank, world, local_rank, args)
+            if rank == 0:
+                extra["prove_sharded"] = ps
 
     if rank == 0:
         peaks = {}
@@ -591,6 +595,38 @@ def bench_prove(ctx, stream, args, with_cpu=True):
     return out
 
 
+def bench_prove_sharded(ctx, dist, rank, world, local_rank, args):
+    """BASELINE.json configs[4] shape: the same prove with every commitment sharded by point range over the ranks
+    (commit-key slice per GPU, 144-byte partial sums all-gathered over NCCL); NTTs and pointwise kernels replicated.
+    Strong scaling: total work fixed.  Timed as the max over ranks."""
+    import torch
+    import plonk_prototype_b200 as pb
+    from plonk_prototype_b200.synth import synthetic_circuit_columns
+    dev = torch.device("cuda", local_rank)
+    out = []
+    for L in sorted(set([args.prove_log_n, args.prove_dist_log_n])):
+        n = 1 << L
+        sel, wires, values, pi_pos, pi_vals = synthetic_circuit_columns(n)
+        sp = pb.ShardedParameters(n, 0xB2000000 + L, rank, world, ctx)
+        pk, _ = ctx.preprocess(sp.srs, sel, wires, values.shape[0], b"pb200-bench", shard=(rank, world, pb.torch_allgather(dist, dev)))
+        proofs = {ctx.prove(sp.srs, pk, values, pi_pos, pi_vals) for _ in range(2)}
+        t = []
+        for _ in range(max(args.steps, 3)):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            proofs.add(ctx.prove(sp.srs, pk, values, pi_pos, pi_vals))
+            dt = torch.tensor([time.perf_counter() - t0], device=dev)
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            t.append(1e3 * float(dt))
+        ctx.prover_key_free(pk)
+        sp.close()
+        out.append({"log_gates": L, "ms": sum(t) / len(t), "min_ms": min(t), "deterministic": len(proofs) == 1, "scaling": "strong"})
+    return {"metric": "sharded PLONK prove, %d GPUs (MSMs by point range + NCCL all-gather of partial commitments)" % world,
+            "unit": "ms", "sizes": out,
+            "parity": "byte-identical with the single-GPU proof (scripts/dist_prove_check.py, profiles/dist_prove_*)"}
+
+
 def gpu_prove_ms(ctx, L):
     import plonk_prototype_b200 as pb
     from plonk_prototype_b200.synth import synthetic_circuit_columns
@@ -622,6 +658,7 @@ def main():
     ap.add_argument("--cpu-sample-log", type=int, default=20, help="log2 of the CPU baseline's bounded sample")
     ap.add_argument("--skip-prove", action="store_true")
     ap.add_argument("--prove-log-n", type=int, default=20, help="log2 of the gate count of the timed PLONK prove")
+    ap.add_argument("--prove-dist-log-n", type=int, default=22, help="log2 of the gate count of the second sharded prove (N > 1)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -207,6 +207,13 @@ PB200_API int pb200_transcript_selftest(const char *label, const char *msg_label
 /* ---- synthetic workloads & measurement helpers (bench.py / tests) -------------- */
 /* bases[i] = (a + i·d)·G, packed affine Montgomery, written to a device buffer of n × 96 B. */
 PB200_API int pb200_synthetic_bases_dev(pb200_ctx *ctx, uint64_t *xy_mont_dev, size_t n, uint64_t a, uint64_t d);
+/* The synthetic arithmetic circuit of SURVEY.md §8d (chain x ← x·x + x + c from mul / add rows, boolean padding, n_pub
+ * public-input rows) written into caller-allocated column images: selectors7 = q_m q_l q_r q_o q_c q_4 q_arith (n_gates × 4
+ * u64 each), wires (n_gates u32 each), values (n_vars × 4 u64; n_vars = 6 + 2·⌊(n_gates − n_pub − 3)/2⌋ + n_pub − 1),
+ * pi_gate / pi_mont (n_pub entries).  Host-side helper for benches and tests; no GPU involved. */
+PB200_API int pb200_synthetic_circuit(size_t n_gates, uint64_t seed, uint32_t n_pub, uint64_t *const selectors7[7], uint32_t *const wires[4],
+                                      uint64_t *values_mont, size_t n_vars_capacity, size_t *n_vars_out, uint32_t *pi_gate,
+                                      uint64_t *pi_mont);
 /* Per-kernel device time of the most recent MSM / NTT call, from CUDA events on the context stream.
  * Known names: "msm.accumulate", "msm.sort", "msm.reduce", "msm.total", "ntt.total".
  * Profiling must have been switched on before that call. */

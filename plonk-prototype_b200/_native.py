@@ -21,7 +21,7 @@ EXPORTS = [
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_batch_dev", "pb200_g1_sum", "pb200_msm_window_bits",
     "pb200_srs_generate", "pb200_srs_generate_range", "pb200_srs_dev_ptr", "pb200_kzg_witness_dev", "pb200_fr_horner_step_dev",
     "pb200_preprocess", "pb200_preprocess_sharded", "pb200_prover_key_free", "pb200_prover_key_size", "pb200_prover_key_bytes", "pb200_prove",
-    "pb200_transcript_selftest",
+    "pb200_transcript_selftest", "pb200_synthetic_circuit",
     "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_launch_count",
     "pb200_imad_peak",
 ]
@@ -107,6 +107,8 @@ def lib():
         L.pb200_prove.argtypes = [vp, vp, vp, u64p, vp, u64p, ctypes.c_size_t, vp]
         L.pb200_transcript_selftest.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
                                                 ctypes.c_char_p, ctypes.c_size_t]
+        L.pb200_synthetic_circuit.argtypes = [ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32, ctypes.POINTER(vp), ctypes.POINTER(vp), u64p,
+                                              ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), vp, u64p]
         L.pb200_synthetic_bases_dev.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64]
         L.pb200_profile_enable.argtypes = [vp, ctypes.c_int]
         L.pb200_profile_ms.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_float)]

@@ -920,3 +920,84 @@ extern "C" int pb200_transcript_selftest(const char *label, const char *msg_labe
     t.challenge_bytes(challenge_label, out, out_len);
     return 0;
 }
+
+// ---- synthetic workload (bench / tests): the circuit of plonk-prototype_b200/synth.py, assembled on the host in C++ so
+// that 2^24 gates take a second instead of a minute.  Same rows, same witness.
+extern "C" int pb200_synthetic_circuit(size_t n_gates, uint64_t seed, uint32_t n_pub, uint64_t *const selectors7[7], uint32_t *const wires[4],
+                                       uint64_t *values_mont, size_t n_vars_capacity, size_t *n_vars_out, uint32_t *pi_gate,
+                                       uint64_t *pi_mont) {
+    if (!selectors7 || !wires || !values_mont || !n_vars_out || n_gates < 8 + (size_t)n_pub || n_pub < 1) return PB200_ERR_ARG;
+    if (n_pub > 1 && (!pi_gate || !pi_mont)) return PB200_ERR_ARG;
+    // SplitMix64 → uniform scalars by rejection
+    uint64_t st = seed;
+    auto next64 = [&]() {
+        uint64_t z = (st += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    HFr consts[4];
+    for (int k = 0; k < 4;) {
+        HFr v;
+        for (int i = 0; i < 4; i++) v.l[i] = next64();
+        v.l[3] &= 0x7fffffffffffffffull;
+        if (!HFr::geq_mod(v.l)) consts[k++] = v * HFr::r2();
+    }
+    const size_t steps = (n_gates - n_pub - 3) / 2, n_bool = n_gates - n_pub - 3 - 2 * steps;
+    const size_t n_vars = 6 + 2 * steps + (n_pub - 1);
+    *n_vars_out = n_vars;
+    if (n_vars > n_vars_capacity) return PB200_ERR_ARG;
+    enum { M, L, R, O, C, F, A };
+    for (int k = 0; k < 7; k++) memset(selectors7[k], 0, n_gates * 32);
+    for (int c = 0; c < 4; c++) memset(wires[c], 0, n_gates * 4);
+    const HFr one = HFr::one(), minus_one = one.neg();
+    auto setq = [&](int col, size_t row, const HFr &v) { v.store(selectors7[col] + 4 * row); };
+    auto setw = [&](size_t row, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+        wires[0][row] = a; wires[1][row] = b; wires[2][row] = c; wires[3][row] = d;
+    };
+    for (size_t i = 0; i < n_gates; i++) setq(A, i, one);
+    HFr *vals = (HFr *)values_mont;
+    vals[0] = HFr::zero();
+    vals[1] = HFr::from_u64(6);
+    vals[2] = one;
+    vals[3] = HFr::from_u64(7);
+    vals[4] = HFr::from_u64(20).neg();
+    vals[5] = consts[0];
+    setq(L, 0, one);
+    setw(1, 1, 3, 4, 2);
+    setq(M, 1, one); setq(L, 1, HFr::from_u64(2)); setq(R, 1, HFr::from_u64(3)); setq(O, 1, HFr::from_u64(4));
+    setq(C, 1, HFr::from_u64(4)); setq(F, 1, one);
+    setw(2, 4, 1, 3, 0);
+    setq(M, 2, one); setq(L, 2, one); setq(R, 2, one); setq(O, 2, one); setq(C, 2, HFr::from_u64(127));
+    HFr x = consts[0], c = consts[1];
+    for (size_t k = 0; k < steps; k++) {
+        const uint32_t xv = (uint32_t)(5 + 2 * k), sq = xv + 1, xn = xv + 2;
+        const size_t r_mul = 3 + 2 * k, r_add = r_mul + 1;
+        const HFr s = x * x;
+        x = s + x + c;
+        vals[sq] = s;
+        vals[xn] = x;
+        setw(r_mul, xv, xv, sq, 0);
+        setq(M, r_mul, one); setq(O, r_mul, minus_one);
+        setw(r_add, sq, xv, xn, 0);
+        setq(L, r_add, one); setq(R, r_add, one); setq(O, r_add, minus_one); setq(C, r_add, c);
+        c = c + one;
+    }
+    const uint32_t x_var = (uint32_t)(5 + 2 * steps);
+    for (size_t r = 3 + 2 * steps; r < 3 + 2 * steps + n_bool; r++) { setq(M, r, one); setq(O, r, minus_one); }
+    for (uint32_t j = 0; j < n_pub; j++) {
+        const size_t row = n_gates - n_pub + j;
+        uint32_t var = x_var;
+        HFr v = x;
+        if (j > 0) {
+            var = (uint32_t)(6 + 2 * steps + (j - 1));
+            vals[var] = consts[2];
+            v = consts[2];
+        }
+        setw(row, var, var, var, 0);
+        setq(L, row, one);
+        pi_gate[j] = (uint32_t)row;
+        v.neg().store(pi_mont + 4 * j);
+    }
+    return 0;
+}

@@ -30,7 +30,30 @@ def _random_fr(seed, n):
 
 
 def synthetic_circuit_columns(n_gates, seed=0x5EED, n_pub=2):
-    """Returns (selectors[11], wires[4], values_mont, pi_pos, pi_vals_mont)."""
+    """Returns (selectors[11], wires[4], values_mont, pi_pos, pi_vals_mont) — assembled by the library's host helper
+    `pb200_synthetic_circuit` (C++; identical rows and witness to `synthetic_circuit_columns_py` below)."""
+    import ctypes
+    from . import _native
+    assert n_gates >= 8 + n_pub and n_pub >= 1
+    steps = (n_gates - n_pub - 3) // 2
+    n_vars = 6 + 2 * steps + n_pub - 1
+    sel7 = [np.empty((n_gates, 4), np.uint64) for _ in range(7)]
+    wires = [np.empty(n_gates, np.uint32) for _ in range(4)]
+    values = np.empty((n_vars, 4), np.uint64)
+    pi_pos, pi_vals = np.empty(n_pub, np.uint32), np.empty((n_pub, 4), np.uint64)
+    sel_ptrs = (ctypes.c_void_p * 7)(*[a.ctypes.data for a in sel7])
+    wire_ptrs = (ctypes.c_void_p * 4)(*[a.ctypes.data for a in wires])
+    got = ctypes.c_size_t()
+    rc = _native.lib().pb200_synthetic_circuit(n_gates, seed, n_pub, sel_ptrs, wire_ptrs, values.ctypes.data, n_vars, ctypes.byref(got),
+                                               pi_pos.ctypes.data, pi_vals.ctypes.data)
+    if rc != 0 or got.value != n_vars:
+        raise _native.Pb200Error("pb200_synthetic_circuit failed (%d)" % rc)
+    sel = [a if a.any() else None for a in sel7] + [None] * 4
+    return sel, wires, values, pi_pos, pi_vals
+
+
+def synthetic_circuit_columns_py(n_gates, seed=0x5EED, n_pub=2):
+    """The same circuit assembled in Python / numpy (the readable definition; used to cross-check the C++ helper)."""
     assert n_gates >= 8 + n_pub
     consts = _random_fr(seed, 4)
     # variables: 0 zero | 1..4 dummy (6, 1, 7, −20) | 5 x_0 | then sq, x' per chain step | extra public-input variables

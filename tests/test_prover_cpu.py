@@ -176,3 +176,22 @@ def test_c_oracle_proof_verifies_at_2k_gates(oracle):
     pts = [pm.bytes_to_g1(vkb[48 * i:48 * i + 48]) for i in range(15)]
     vk = {"n": 2048, "q": dict(zip(pm.SELECTORS, pts[:11])), "sigma": pts[11:]}
     assert pm.verify(vk, proof, comp.pi, pm.opening_key(tau), label)
+
+
+def test_cxx_synthetic_circuit_helper_matches_python_definition_and_model():
+    """pb200_synthetic_circuit (host C++ in libpb200.so, no GPU) builds the same columns as the numpy definition and as
+    driving the model composer gate by gate."""
+    import plonk_prototype_b200 as pb
+    from plonk_prototype_b200.synth import synthetic_circuit_columns, synthetic_circuit_columns_py
+    for ng, npub in ((13, 2), (30, 3), (257, 1), (1000, 2)):
+        a, b = synthetic_circuit_columns(ng, n_pub=npub), synthetic_circuit_columns_py(ng, n_pub=npub)
+        for k in range(11):
+            assert (a[0][k] is None) == (b[0][k] is None)
+            assert a[0][k] is None or (a[0][k] == b[0][k]).all()
+        assert all((x == y).all() for x, y in zip(a[1], b[1]))
+        assert (a[2] == b[2]).all() and (a[3] == b[3]).all() and (a[4] == b[4]).all()
+    comp = pm.synthetic_circuit(30, n_pub=3)
+    sel, wires, values, pi_pos, pi_vals = synthetic_circuit_columns(30, n_pub=3)
+    assert [list(w) for w in wires] == comp.w
+    assert (values == pb.scalars_to_mont(comp.values)).all()
+    assert list(pi_pos) == sorted(comp.pi)
