@@ -200,6 +200,18 @@ PB200_API int pb200_preprocess_sharded(pb200_ctx *ctx, const pb200_srs *srs_slic
  * With profiling on, pb200_profile_ms knows "prove.round1" … "prove.round5" (host wall-clock per round). */
 PB200_API int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk, const uint64_t *values_mont,
                           const uint32_t *pi_gate, const uint64_t *pi_mont, size_t n_pi, uint8_t proof_out[1040]);
+/* ---- verifier (host CPU, as upstream's): dusk_plonk Proof::verify + OpeningKey::batch_check + the BLS12-381 pairing of
+ * dusk_bls12_381.  No context and no GPU: the work is milliseconds and independent of n. ------- */
+/* vk_commitments: the 15 compressed commitments pb200_preprocess returns; n: padded circuit size; public inputs as for
+ * pb200_prove; beta_h: the opening key's β·H ∈ G2, affine x.c0 ‖ x.c1 ‖ y.c0 ‖ y.c1 (4 × 6 u64, Montgomery).
+ * Returns 0 with *accepted = 1 / 0 (a malformed proof is a rejection, not an error); PB200_ERR_ARG for bad arguments. */
+PB200_API int pb200_verify(const uint8_t vk_commitments[15 * 48], size_t n, const uint8_t *transcript_label, size_t label_len,
+                           const uint8_t proof[1040], const uint32_t *pi_gate, const uint64_t *pi_mont, size_t n_pi,
+                           const uint64_t beta_h[24], int *accepted);
+/* β·H for parameters generated from a known trapdoor (pb200_srs_generate): the G2 half of PublicParameters::setup. */
+PB200_API int pb200_opening_key_from_tau(const uint64_t tau_mont[4], uint64_t beta_h_out[24]);
+/* Pairing self-check without a known-answer table: e(a·G1, b·G2) = e(G1, G2)^(ab) ≠ 1. */
+PB200_API int pb200_pairing_selftest(const uint64_t a_mont[4], const uint64_t b_mont[4], int *ok);
 /* merlin::Transcript known-answer hook: Transcript::new(label); append_message(msg_label, msg); challenge_bytes(ch_label). */
 PB200_API int pb200_transcript_selftest(const char *label, const char *msg_label, const uint8_t *msg, size_t msg_len,
                                         const char *challenge_label, uint8_t *out, size_t out_len);

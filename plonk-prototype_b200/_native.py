@@ -21,7 +21,8 @@ EXPORTS = [
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_batch_dev", "pb200_g1_sum", "pb200_msm_window_bits",
     "pb200_srs_generate", "pb200_srs_generate_range", "pb200_srs_dev_ptr", "pb200_kzg_witness_dev", "pb200_fr_horner_step_dev",
     "pb200_preprocess", "pb200_preprocess_sharded", "pb200_prover_key_free", "pb200_prover_key_size", "pb200_prover_key_bytes", "pb200_prove",
-    "pb200_transcript_selftest", "pb200_synthetic_circuit",
+    "pb200_transcript_selftest", "pb200_synthetic_circuit", "pb200_verify", "pb200_opening_key_from_tau",
+    "pb200_pairing_selftest",
     "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_launch_count",
     "pb200_imad_peak",
 ]
@@ -107,6 +108,10 @@ def lib():
         L.pb200_prove.argtypes = [vp, vp, vp, u64p, vp, u64p, ctypes.c_size_t, vp]
         L.pb200_transcript_selftest.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
                                                 ctypes.c_char_p, ctypes.c_size_t]
+        L.pb200_verify.argtypes = [vp, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, vp, vp, u64p, ctypes.c_size_t, u64p,
+                                   ctypes.POINTER(ctypes.c_int)]
+        L.pb200_opening_key_from_tau.argtypes = [u64p, u64p]
+        L.pb200_pairing_selftest.argtypes = [u64p, u64p, ctypes.POINTER(ctypes.c_int)]
         L.pb200_synthetic_circuit.argtypes = [ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint32, ctypes.POINTER(vp), ctypes.POINTER(vp), u64p,
                                               ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), vp, u64p]
         L.pb200_synthetic_bases_dev.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64]
@@ -125,6 +130,31 @@ def _ptr(a):
         assert a.flags["C_CONTIGUOUS"]
         return ctypes.c_void_p(a.ctypes.data)
     return ctypes.c_void_p(int(a))
+
+
+def opening_key_from_tau(tau_mont):
+    """β·H ∈ G2 (24 u64) for a trapdoor-generated SRS — host only, no GPU."""
+    tau = np.ascontiguousarray(tau_mont, dtype=np.uint64).reshape(4)
+    out = np.zeros(24, np.uint64)
+    if lib().pb200_opening_key_from_tau(_ptr(tau), _ptr(out)) != 0:
+        raise Pb200Error("pb200_opening_key_from_tau failed")
+    return out
+
+
+def verify(vk_bytes, n, label, proof, pi_gate, pi_mont, beta_h):
+    """`Proof::verify` on the host CPU (csrc/verify.cu).  Returns True / False."""
+    vk = np.frombuffer(bytes(vk_bytes), dtype=np.uint8).copy()
+    pr = np.frombuffer(bytes(proof), dtype=np.uint8).copy()
+    assert vk.size == 720 and pr.size == 1040
+    pos = np.ascontiguousarray(pi_gate, dtype=np.uint32)
+    piv = np.ascontiguousarray(pi_mont, dtype=np.uint64).reshape(-1, 4)
+    bh = np.ascontiguousarray(beta_h, dtype=np.uint64).reshape(24)
+    ok = ctypes.c_int(0)
+    rc = lib().pb200_verify(_ptr(vk), n, bytes(label), len(label), _ptr(pr), _ptr(pos) if pos.size else None,
+                            _ptr(piv) if pos.size else None, pos.shape[0], _ptr(bh), ctypes.byref(ok))
+    if rc != 0:
+        raise Pb200Error("pb200_verify: bad argument (%d)" % rc)
+    return bool(ok.value)
 
 
 class Context:

@@ -84,8 +84,15 @@ def test_proof_accepted_by_pairing_verifier(ctx, n_gates):
     vk = vk_from_bytes(vkb, n)
     ok = pm.opening_key(tau)
     assert pm.verify(vk, proof, comp.pi, ok, label)
+    # the library's own verifier (csrc/verify.cu) agrees
+    import plonk_prototype_b200 as pb
+    items = sorted(comp.pi.items())
+    pos, piv = np.asarray([p for p, _ in items], dtype=np.uint32), mont([v for _, v in items])
+    bh = pb.opening_key_from_tau(mont([tau]))
+    assert pb.verify(vkb, n, label, proof, pos, piv, bh)
     bad = bytearray(proof)
     bad[528 + 5] ^= 0x10                                   # a_eval
+    assert not pb.verify(vkb, n, label, bytes(bad), pos, piv, bh)
     assert not pm.verify(vk, bytes(bad), comp.pi, ok, label)
     bad = bytearray(proof)
     bad[48 * 4 + 20] ^= 0x01                               # z_comm (almost surely not a curve point any more)
@@ -125,6 +132,7 @@ def test_full_size_proof_2_20_gates_accepted_by_pairing_verifier(ctx):
     rinv = pow(model.FR_MONT_R, -1, model.R)
     pi = {int(p): model.from_limbs(v) * rinv % model.R for p, v in zip(pi_pos, pi_vals)}
     assert pm.verify(vk_from_bytes(vkb, n), proof, pi, pm.opening_key(tau), label)
+    assert pb.verify(vkb, n, label, proof, pi_pos, pi_vals, pb.opening_key_from_tau(pb.scalars_to_mont([tau])))
     bad = bytearray(proof)
     bad[1039] ^= 0x01
     assert not pm.verify(vk_from_bytes(vkb, n), bytes(bad), pi, pm.opening_key(tau), label)
