@@ -195,6 +195,12 @@ def run_reference(args, rank, world):
                                    "here (no cargo, crates not vendored)" % (sample_log, cores)},
         "e2e": {"value": value, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.skip_prove:
+        # the CPU prover on a bounded circuit (2^16 gates: seconds), same restatement as the `prove.cpu_baseline` of our arm
+        cl = min(args.prove_log_n, 16)
+        t_pre, t_prove = cpu_prove_sample(cl, cores)
+        line["prove"] = {"metric": "PLONK prove, synthetic arithmetic circuit, 2^%d gates, CPU restatement" % cl, "value": 1e3 * t_prove,
+                         "unit": "ms", "preprocess_ms": 1e3 * t_pre, "cores": cores, "kind": "port"}
     print(json.dumps(line), flush=True)
 
 

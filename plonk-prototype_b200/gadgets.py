@@ -1,0 +1,112 @@
+"""The reference's own gadgets and circuit, restated over the `StandardComposer` mirror so that they can be proved
+through this backend: /root/reference/src/zk/gadgets.rs (`maybe_equal` :49-84, `range_check` :94-109, `min_bound`
+:120-145, `max_bound` :151-184, `scalar_decomposition_gadget` :186-225, `scalar_to_bits` :228-237, `bits_count`
+:240-248, `num_bits_closest_power_of_two` :252-256), /root/reference/src/zk/allocated_scalar.rs:25-38 and
+`MockCircuit::valid_balance` (/root/reference/src/zk/circuits.rs:51-60).
+
+These functions only append rows to the composer (host-side bookkeeping, as in the reference); behaviours a maintainer
+would expect to carry over are kept on purpose: the decomposition allocates all 256 bit variables before truncating,
+`min_bound` / `max_bound` pass a zero coefficient on the witness as their right operand, `max_bound` subtracts one from
+the bound first, and `bits_count` works on the canonical value starting from one.
+
+Not available: `commitment_gadget`, `MockCircuit::prove_ownership` and `check_hash_inputs` need the fixed-base /
+variable-base group-add widgets and dusk-poseidon's round constants, which this backend does not implement
+(pb200_preprocess rejects those selector columns) — they raise NotImplementedError rather than build a wrong circuit.
+"""
+from .prover import R
+
+
+class AllocatedScalar:
+    """A variable together with its witness assignment (allocated_scalar.rs:25-38)."""
+
+    def __init__(self, var, scalar):
+        self.var, self.scalar = var, scalar % R
+
+    @classmethod
+    def allocate(cls, composer, scalar):
+        return cls(composer.add_input(scalar), scalar)
+
+
+def scalar_to_bits(scalar):
+    """256 little-endian bits of the canonical value (bit i of byte k = bit 8k + i)."""
+    return [(scalar % R >> i) & 1 for i in range(256)]
+
+
+def bits_count(scalar):
+    scalar %= R
+    counter = 1
+    while scalar > 1:
+        scalar >>= 1
+        counter += 1
+    return counter
+
+
+def num_bits_closest_power_of_two(scalar):
+    return bits_count(pow(2, bits_count(scalar), R))
+
+
+def maybe_equal(composer, a, b):
+    """1 if a = b, 0 otherwise: u = a − b, z = u⁻¹ (0 for 0), y = 1 − u·z, and y·u = 0."""
+    u = composer.add((1, a.var), (-1, b.var), 0, None)
+    u_scalar = (a.scalar - b.scalar) % R
+    z = composer.add_input(pow(u_scalar, -1, R) if u_scalar else 0)
+    y = composer.mul(-1, z, u, 1, None)
+    composer.mul_gate(y, u, u, 1, 0, 0, None)
+    return y
+
+
+def scalar_decomposition_gadget(composer, num_bits, witness):
+    bits = scalar_to_bits(witness.scalar)
+    bit_vars = [composer.add_input(bit) for bit in bits][:num_bits]   # all 256 are allocated, then truncated
+    acc = AllocatedScalar(composer.add_witness_to_circuit_description(0), 0)
+    for power, bit in enumerate(bit_vars):
+        composer.boolean_gate(bit)
+        two_pow = pow(2, power, R)
+        acc.var = composer.add((two_pow, bit), (1, acc.var), 0, None)
+        acc.scalar = (acc.scalar + two_pow * bits[power]) % R
+    return maybe_equal(composer, acc, witness), bit_vars
+
+
+def range_proof(composer, value, num_bits):
+    is_equal, _ = scalar_decomposition_gadget(composer, num_bits, value)
+    return is_equal
+
+
+def min_bound(composer, min_range, witness, num_bits):
+    """1 if witness ≥ min_range (as num_bits-bit quantities), else 0."""
+    var = composer.add((1, witness.var), (0, witness.var), -min_range, None)
+    return range_proof(composer, AllocatedScalar(var, witness.scalar - min_range), num_bits)
+
+
+def max_bound(composer, max_range, witness):
+    """(1 if witness < max_range else 0, number of bits used)."""
+    max_range = (max_range - 1) % R
+    num_bits = num_bits_closest_power_of_two(max_range)
+    var = composer.add((-1, witness.var), (0, witness.var), max_range, None)
+    return range_proof(composer, AllocatedScalar(var, max_range - witness.scalar), num_bits), num_bits
+
+
+def range_check(composer, min_range, max_range, witness):
+    y1, num_bits = max_bound(composer, max_range, witness)
+    y2 = min_bound(composer, min_range, witness, num_bits)
+    return composer.mul(1, y1, y2, 0, None)
+
+
+def commitment_gadget(composer, value, blinder):
+    raise NotImplementedError("fixed_base_scalar_mul / point_addition_gate need the group-add widgets, which are not implemented")
+
+
+class MockCircuit:
+    def __init__(self, note_value, private_key=None, hash_inputs=(), public_key=None):
+        self.note_value, self.private_key, self.hash_inputs, self.public_key = note_value, private_key, list(hash_inputs), public_key
+
+    def valid_balance(self, composer, tx_value, gas_fee):
+        """The note value covers the transaction and its gas: min_bound(tx + gas, note, 30 bits).  As in the reference the
+        0/1 output is returned to the caller and not itself constrained."""
+        return min_bound(composer, (tx_value + gas_fee) % R, self.note_value, 30)
+
+    def prove_ownership(self, composer):
+        raise NotImplementedError("fixed_base_scalar_mul needs the fixed-base group-add widget, which is not implemented")
+
+    def check_hash_inputs(self, composer, public_hash):
+        raise NotImplementedError("dusk-poseidon's sponge gadget (round constants not available offline) is not implemented")

@@ -241,3 +241,43 @@ def test_library_verifier_agrees_with_model_on_golden_proofs():
         non_canonical = bytearray(proof)
         non_canonical[528:560] = (int.from_bytes(proof[528:560], "little") + model.R).to_bytes(32, "little")
         assert not pb.verify(vk, case["n"], label, bytes(non_canonical), pos, piv, bh)
+
+
+# ---------------------------------------------------------------------------------------------- the reference's gadgets
+def test_reference_gadget_semantics_on_the_composer_mirror():
+    """gadgets.rs / circuits.rs restated (plonk-prototype_b200/gadgets.py): outputs and row counts of the reference's
+    arithmetic gadgets (min_bound with 30 bits ≈ 65 gates)."""
+    import plonk_prototype_b200 as pb
+    G = pb.gadgets
+    assert [G.bits_count(v) for v in (0, 1, 2, 3, 4, 255, 256)] == [1, 1, 2, 2, 3, 8, 9]
+    assert G.num_bits_closest_power_of_two(1000) == 11
+    bits = G.scalar_to_bits(0b1011)
+    assert bits[:5] == [1, 1, 0, 1, 0] and len(bits) == 256
+
+    def run(note, tx, gas):
+        cs = pb.StandardComposer()
+        before_rows, before_vars = cs.n, len(cs.variables)
+        out = G.MockCircuit(G.AllocatedScalar.allocate(cs, note)).valid_balance(cs, tx, gas)
+        return cs, cs.variables[out], cs.n - before_rows, len(cs.variables) - before_vars
+
+    cs, out, rows, nvars = run(1000, 700, 50)
+    assert out == 1 and rows == 1 + 1 + 2 * 30 + 3            # add, zero constraint, (boolean + add) per bit, maybe_equal
+    assert nvars == 1 + 1 + 256 + 1 + 30 + 3                  # note, x−a, 256 bits, accumulator zero, 30 sums, u z y
+    assert run(700, 700, 50)[1] == 0                          # 700 − 750 wraps: not a 30-bit quantity
+    assert run(750, 700, 50)[1] == 1
+
+    # every row of the built circuit is satisfied (the same check the model composer does)
+    v = cs.variables
+    for i in range(cs.n):
+        a, b, c, d = v[cs.w_l[i]], v[cs.w_r[i]], v[cs.w_o[i]], v[cs.w_4[i]]
+        q = {k: cs.q[k][i] for k in cs.q}
+        t = q["q_arith"] * (q["q_m"] * a * b + q["q_l"] * a + q["q_r"] * b + q["q_o"] * c + q["q_4"] * d + q["q_c"])
+        assert (t + cs.public_inputs_sparse_store.get(i, 0)) % model.R == 0, i
+
+    cs2 = pb.StandardComposer()
+    w = G.AllocatedScalar.allocate(cs2, 500)
+    assert cs2.variables[G.range_check(cs2, 100, 1000, w)] == 1
+    cs3 = pb.StandardComposer()
+    assert cs3.variables[G.range_check(cs3, 100, 1000, G.AllocatedScalar.allocate(cs3, 1000))] == 0   # max is exclusive
+    with pytest.raises(NotImplementedError):
+        G.commitment_gadget(cs3, 0, 0)
