@@ -138,6 +138,81 @@ def test_full_size_proof_2_20_gates_accepted_by_pairing_verifier(ctx):
     assert not pm.verify(vk_from_bytes(vkb, n), bytes(bad), pi, pm.opening_key(tau), label)
 
 
+def tiny_circuit(n_gates, n_pub):
+    """The composer's 3 fixed rows plus boolean rows on fresh variables and public-input rows: any size ≥ 3."""
+    comp = pm.Composer()
+    k = 0
+    while comp.n < n_gates - n_pub:
+        comp.boolean_gate(comp.add_input(k & 1))
+        k += 1
+    for j in range(n_pub):
+        v = comp.add_input(1000 + j)
+        comp.constrain_to_constant(v, 0, -(1000 + j))
+    assert comp.n == n_gates and comp.check()
+    return comp
+
+
+@pytest.mark.parametrize("n_gates,n_pub", [(3, 0), (4, 1), (5, 0), (7, 2), (8, 0), (9, 1), (15, 3), (16, 0), (16, 2), (17, 1), (31, 0), (32, 4),
+                                           (33, 0), (63, 1), (64, 0), (65, 2), (127, 0), (128, 3), (129, 1), (255, 0), (256, 2), (257, 0)])
+def test_edge_sizes_byte_identical_with_c_restatement(ctx, oracle, n_gates, n_pub):
+    """Ragged and exact power-of-two gate counts, with and without public inputs (domains 4 … 512: every NTT plan from the
+    single-pass kernel up, MSMs below the 32-point window switch of upstream)."""
+    from test_prover_cpu import c_oracle_prove
+    tau, label = 0xED6E + n_gates, b"edge"
+    comp = tiny_circuit(n_gates, n_pub)
+    proof, vk = gpu_prove(ctx, comp, tau, label)
+    want_proof, want_vk = c_oracle_prove(oracle, comp, tau, label, threads=2)
+    assert vk == want_vk
+    assert proof == want_proof
+
+
+def test_new_witness_same_key(ctx, oracle):
+    """Prover::prove again with another assignment of the same circuit (the key is reused, as upstream's ProverKey is)."""
+    import plonk_prototype_b200 as pb
+    from test_prover_cpu import c_oracle_prove
+    tau, label = 0xAB, b"rewitness"
+    comp = tiny_circuit(40, 2)
+    pp = pb.PublicParameters(63, tau, ctx)
+    sel, wires = columns(comp)
+    pk, _ = ctx.preprocess(pp.srs, sel, wires, len(comp.values), label)
+    pis = sorted(comp.pi.items())
+    pos, piv = np.asarray([p for p, _ in pis], dtype=np.uint32), mont([v for _, v in pis])
+    proofs = []
+    for flip in (False, True):
+        if flip:                                                   # every boolean input inverted: still satisfies the same rows
+            for i in range(3, comp.n - 2):
+                v = comp.w[0][i]
+                comp.values[v] = 1 - comp.values[v]
+            assert comp.check()
+        got = ctx.prove(pp.srs, pk, mont(comp.values), pos, piv)
+        want, _ = c_oracle_prove(oracle, comp, tau, label)
+        assert got == want
+        proofs.append(got)
+    assert proofs[0] != proofs[1]
+    ctx.prover_key_free(pk)
+    pp.close()
+
+
+def test_argument_errors_are_reported_not_crashed(ctx):
+    import plonk_prototype_b200 as pb
+    comp = pm.synthetic_circuit(13)
+    sel, wires = columns(comp)
+    small = pb.PublicParameters(7, 5, ctx)                              # 8 points for a 16-row circuit
+    with pytest.raises(pb.Pb200Error):
+        ctx.preprocess(small.srs, sel, wires, len(comp.values), b"x")
+    small.close()
+    pp = pb.PublicParameters(15, 5, ctx)
+    bad_wires = [w.copy() for w in wires]
+    bad_wires[2][5] = len(comp.values) + 3                              # unallocated variable
+    with pytest.raises(pb.Pb200Error):
+        ctx.preprocess(pp.srs, sel, bad_wires, len(comp.values), b"x")
+    pk, _ = ctx.preprocess(pp.srs, sel, wires, len(comp.values), b"x")
+    with pytest.raises(pb.Pb200Error):                                  # public input outside the domain
+        ctx.prove(pp.srs, pk, mont(comp.values), np.asarray([16], dtype=np.uint32), mont([1]))
+    ctx.prover_key_free(pk)
+    pp.close()
+
+
 def test_bad_witness_is_rejected_by_verifier(ctx):
     tau, label = 0xBAD, b"pb200-verify"
     comp = pm.synthetic_circuit(200)
