@@ -550,7 +550,11 @@ def bench_prove(ctx, stream, args, with_cpu=True):
     from plonk_prototype_b200.synth import synthetic_circuit_columns
     L = args.prove_log_n
     n = 1 << L
+    import torch
     sel, wires, values, pi_pos, pi_vals = synthetic_circuit_columns(n)
+    pinned = torch.empty(values.shape, dtype=torch.int64, pin_memory=True)   # the witness comes from pinned host memory
+    pinned.numpy().view(np.uint64)[:] = values
+    values = pinned.numpy().view(np.uint64)
     pp = pb.PublicParameters(n - 1, 0xB2000000 + L, ctx)
     t0 = time.perf_counter()
     pk, vk = ctx.preprocess(pp.srs, sel, wires, values.shape[0], b"pb200-bench")
@@ -577,7 +581,7 @@ def bench_prove(ctx, stream, args, with_cpu=True):
            "deterministic": len(proofs) == 1, "prover_key_gib": ctx.prover_key_bytes(pk) / 2**30,
            "e2e": {"value": sum(t) / len(t), "unit": "ms", "h2d_bytes_per_step": int(values.nbytes + pi_vals.nbytes + pi_pos.nbytes),
                    "d2h_bytes_per_step": 1040 + 11 * 144 + 17 * 32,
-                   "note": "pb200_prove is the end-to-end call: witness values from host memory, proof bytes on the host"},
+                   "note": "pb200_prove is the end-to-end call: witness values from pinned host memory, proof bytes on the host"},
            "parity": "proofs byte-identical with the CPU restatement up to 2^13 gates and accepted by the pairing verifier "
                      "up to 2^20 gates (tests/test_prover_gpu.py); parity unpinned against the Rust reference (not buildable here)"}
     ctx.prover_key_free(pk)

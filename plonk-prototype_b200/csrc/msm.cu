@@ -163,10 +163,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
 }
 
 // Level 1: entries (bucket id, point index | sign) → buckets / partial slots, mixed additions.
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine *__restrict__ bases, const uint2 *__restrict__ entries,
-                                                             const uint32_t *__restrict__ n_entries_ptr, uint32_t L,
-                                                             G1Xyzz *buckets, uint32_t *out_gb, G1Xyzz *out_pt,
-                                                             uint32_t *n_out_ptr) {
+__device__ __forceinline__ void msm_accumulate_body(const G1Affine *__restrict__ bases, const uint2 *__restrict__ entries,
+                                                    const uint32_t *__restrict__ n_entries_ptr, uint32_t L, G1Xyzz *buckets,
+                                                    uint32_t *out_gb, G1Xyzz *out_pt, uint32_t *n_out_ptr) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t M = *n_entries_ptr;
     if (t == 0) *n_out_ptr = 2 * ((M + L - 1) / L);
@@ -201,6 +200,11 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine *__r
     }
     sink.flush(cur, acc, tl, next == cur);
     sink.finish();
+}
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine *__restrict__ bases, const uint2 *__restrict__ entries,
+                                                             const uint32_t *__restrict__ n_entries_ptr, uint32_t L, G1Xyzz *buckets,
+                                                             uint32_t *out_gb, G1Xyzz *out_pt, uint32_t *n_out_ptr) {
+    msm_accumulate_body(bases, entries, n_entries_ptr, L, buckets, out_gb, out_pt, n_out_ptr);
 }
 // Window width with pre-doubled copies: one shared bucket set, so only W·n additions + one reduction of 2^(c−1) buckets.
 uint32_t choose_window_pre(size_t n) {

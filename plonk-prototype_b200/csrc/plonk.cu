@@ -197,10 +197,10 @@ struct QuotArgs {
     const Fr *sig;       // 4 × N4
     const Fr *lin;       // X on the coset: 7·ω_4n^i
     const Fr *w;         // a, b, c, d: 4 × N4
-    const Fr *z, *pi, *l1;
+    const Fr *z, *pi, *l1;  // l1: L₁ on the coset (unscaled)
     Fr *out;
     uint32_t N4;
-    Fr alpha, beta, gamma, range_sep;
+    Fr alpha, alpha2, beta, gamma, range_sep;
     Fr vh_inv[4];        // 1 / ((7ω_4n^i)^n − 1) has period 4 in i
     KFactors ks;
 };
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(const QuotArgs A) {
     Fr cp = (ag + A.beta * ld_fr(A.sig + i)) * (bg + A.beta * ld_fr(A.sig + (size_t)N4 + i));
     cp = cp * ((cg + A.beta * ld_fr(A.sig + 2 * (size_t)N4 + i)) * (dg + A.beta * ld_fr(A.sig + 3 * (size_t)N4 + i)));
     cp = cp * zn;
-    Fr t = (id - cp) * A.alpha + (zi - Fr::one()) * ld_fr(A.l1 + i);
+    Fr t = (id - cp) * A.alpha + ((zi - Fr::one()) * ld_fr(A.l1 + i)) * A.alpha2;
     st_fr(A.out + i, (g + t) * A.vh_inv[i & 3]);
 }
 
@@ -337,7 +337,7 @@ struct pb200_prover_key {
     size_t slab_bytes = 0;
     Fr *q_poly[kSel] = {}, *q_4n[kSel] = {};
     Fr *sig_evals = nullptr, *sig_poly = nullptr, *sig_4n = nullptr;  // 4·n, 4·n, 4·4n
-    Fr *roots = nullptr, *lin_4n = nullptr;
+    Fr *roots = nullptr, *lin_4n = nullptr, *l1_4n = nullptr;  // ω^i | X on the coset | L₁ on the coset
     uint32_t *wires = nullptr;
     // prove workspace
     Fr *values = nullptr, *w_evals = nullptr, *w_poly = nullptr, *z_poly = nullptr, *pi_poly = nullptr, *ev4 = nullptr, *t_poly = nullptr,
@@ -383,13 +383,14 @@ void carve(pb200_prover_key *pk, void *base, size_t *total) {
     pk->sig_4n = c.take<Fr>(4 * N4);
     pk->roots = c.take<Fr>(n);
     pk->lin_4n = c.take<Fr>(N4);
+    pk->l1_4n = c.take<Fr>(N4);
     pk->wires = c.take<uint32_t>(4 * pk->n_gates);
     pk->values = c.take<Fr>(pk->n_vars);
     pk->w_evals = c.take<Fr>(4 * n);
     pk->w_poly = c.take<Fr>(4 * n);
     pk->z_poly = c.take<Fr>(n);
     pk->pi_poly = c.take<Fr>(n);
-    pk->ev4 = c.take<Fr>(7 * N4);  // a, b, c, d | z | pi | α²·L1 on the coset
+    pk->ev4 = c.take<Fr>(6 * N4);  // a, b, c, d | z | pi on the coset
     pk->t_poly = c.take<Fr>(N4);
     pk->lin_poly = c.take<Fr>(n);
     pk->agg = c.take<Fr>(n);
@@ -623,6 +624,10 @@ extern "C" int pb200_preprocess_sharded(pb200_ctx *ctx, const pb200_srs *srs, co
     PK_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)pk->sig_poly, log_n, 4, 1, 0));
     PK_TRY(commit_bytes_batch(ctx, srs, pk, pk->sig_poly, n, 4, n, vk + 48 * kSel));
     PK_TRY(coset_extend(ctx, pk->sig_4n, pk->sig_poly, (uint32_t)n, log_n + 2, 4));
+    // L₁ on the coset (its n coefficients are all 1/n): circuit-independent, so the prover only scales it by α²
+    fill_kernel<<<cdiv(n, 256), 256, 0, st>>>(pk->lin_poly, (uint32_t)n, to_dev(HFr::from_u64(n).inv()));
+    PK_LAUNCHED();
+    PK_TRY(coset_extend(ctx, pk->l1_4n, pk->lin_poly, (uint32_t)n, log_n + 2, 1));
     PK_CUDA(cudaStreamSynchronize(st));
 
     // Transcript::new(label) seeded with the verifier key
@@ -713,17 +718,11 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
         PB_LAUNCHED(ctx);
         PB_TRY(pb200_ntt_dev(ctx, (uint64_t *)pk->pi_poly, log_n, 1, 0));
     }
-    // coset evaluations on 4n: a, b, c, d | z | pi | α²·L1 (L1's coefficients are all 1/n)
-    Fr *w4 = pk->ev4, *z4 = pk->ev4 + 4 * N4, *pi4 = z4 + N4, *l14 = pi4 + N4;
+    // coset evaluations on 4n: a, b, c, d | z | pi   (L₁ is kept from preprocessing)
+    Fr *w4 = pk->ev4, *z4 = pk->ev4 + 4 * N4, *pi4 = z4 + N4;
     PB_TRY(coset_extend(ctx, w4, pk->w_poly, n32, log_n + 2, 4));
     PB_TRY(coset_extend(ctx, z4, pk->z_poly, n32, log_n + 2, 1));
     PB_TRY(coset_extend(ctx, pi4, pk->pi_poly, n32, log_n + 2, 1));
-    {
-        const HFr n_inv = HFr::from_u64(n).inv();
-        fill_kernel<<<cdiv(n, 256), 256, 0, st>>>(pk->lin_poly, n32, to_dev(alpha.sqr() * n_inv));
-        PB_LAUNCHED(ctx);
-        PB_TRY(coset_extend(ctx, l14, pk->lin_poly, n32, log_n + 2, 1));
-    }
     {
         QuotArgs A;
         for (int s = 0; s < kSel; s++) A.q[s] = pk->q_4n[s];
@@ -732,7 +731,8 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
         A.w = w4;
         A.z = z4;
         A.pi = pi4;
-        A.l1 = l14;
+        A.l1 = pk->l1_4n;
+        A.alpha2 = to_dev(alpha.sqr());
         A.out = pk->t_poly;
         A.N4 = (uint32_t)N4;
         A.alpha = to_dev(alpha);
