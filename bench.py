@@ -406,6 +406,7 @@ def bench_ntt_sharded(ctx, dist, rank, world, args):
     shard = random_fr_limbs(0xF1F00000 + L + 1000 * rank, spec.local)
     buf = torch.from_numpy(shard.view(np.int64).reshape(-1).copy()).cuda()
     tmp = torch.empty_like(buf)
+    torch.cuda.synchronize()   # `buf` was filled on torch's stream
     dom.fft(buf, tmp)
     dom.ifft(buf, tmp)
     ctx.sync(); torch.cuda.synchronize()
@@ -437,6 +438,7 @@ def bench_ntt_sharded(ctx, dist, rank, world, args):
     fused_ms = sorted(ts)[len(ts) // 2]
     # the fused result must equal the NCCL result (itself checked against the single-GPU transform in tests)
     buf.copy_(col)
+    torch.cuda.synchronize()   # the copy runs on torch's stream, the transform on the library's
     dom.fft(buf, tmp)
     ctx.sync(); torch.cuda.synchronize()
     fused_out = np.empty((spec.local, 4), np.uint64)
@@ -451,7 +453,7 @@ def bench_ntt_sharded(ctx, dist, rank, world, args):
             "value": (1 << L) / (ms * 1e-3) / 1e6, "unit": "Melem/s", "scaling": "strong", "n1": spec.n1,
             "fused_peer_store_ms": fused_ms, "nccl_all_to_all_ms": nccl_ms,
             "exchange_bytes_per_gpu": spec.local * 32 * (world - 1) // world,
-            "verified": bad == 0.0, "note": "fused: column kernel writes the owners' row buffers over NVLink peer memory, "
+            "verified": bad == 0.0, "roundtrip_ok": ok, "fused_equals_nccl": same, "note": "fused: column kernel writes the owners' row buffers over NVLink peer memory, "
             "wall clock incl. the cross-rank barrier; nccl: column kernel + all_to_all_single + transpose kernel, CUDA events"}
 
 
