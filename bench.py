@@ -620,7 +620,7 @@ def bench_prove_sharded(ctx, dist, rank, world, local_rank, args):
         n = 1 << L
         sel, wires, values, pi_pos, pi_vals = synthetic_circuit_columns(n)
         sp = pb.ShardedParameters(n, 0xB2000000 + L, rank, world, ctx)
-        pk, _ = ctx.preprocess(sp.srs, sel, wires, values.shape[0], b"pb200-bench", shard=(rank, world, pb.torch_allgather(dist, dev)))
+        pk, _ = ctx.preprocess(sp.srs, sel, wires, values.shape[0], b"pb200-bench", shard=(rank, world, pb.torch_allgather(dist, dev)) + pb.torch_device_collectives(dist, dev))
         proofs = {ctx.prove(sp.srs, pk, values, pi_pos, pi_vals) for _ in range(2)}
         t = []
         for _ in range(max(args.steps, 3)):

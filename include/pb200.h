@@ -184,10 +184,20 @@ PB200_API size_t pb200_prover_key_bytes(const pb200_prover_key *pk); /* device m
  * kernels run replicated on every rank (they are ~15 % of a single-GPU prove).  The callback receives `bytes` bytes in
  * `send` and must fill `recv` with world × bytes, rank-major; non-zero return aborts the call. */
 typedef int (*pb200_allgather_fn)(void *user, const void *send, void *recv, size_t bytes);
+/* Optional device-memory collectives (NCCL over NVLink).  When both are given, round 3 — seven coset transforms of 4n
+ * points, the quotient kernel and the inverse transform — is sharded too: four-step transforms with this rank owning a
+ * column range of the coefficient side and a row range of the evaluation side (one all-to-all each, as in
+ * pb200_ntt_columns_dev), the quotient evaluated on the local rows, and one all-gather of t(X)'s coefficient shards.
+ * alltoall_dev: block h (bytes_per_peer bytes) of send_dev goes to rank h, block b of recv_dev comes from rank b.
+ * allgather_dev: recv_dev = world × bytes, rank-major.  Both must have completed when they return. */
+typedef int (*pb200_alltoall_dev_fn)(void *user, const void *send_dev, void *recv_dev, size_t bytes_per_peer);
+typedef int (*pb200_allgather_dev_fn)(void *user, const void *send_dev, void *recv_dev, size_t bytes);
 typedef struct pb200_shard {
     uint32_t rank, world;
     pb200_allgather_fn allgather;
     void *user;
+    pb200_alltoall_dev_fn alltoall_dev;   /* may be NULL: NTTs and the quotient kernel then run replicated */
+    pb200_allgather_dev_fn allgather_dev; /* may be NULL */
 } pb200_shard;
 /* As pb200_preprocess, with `srs` holding this rank's slice.  The shard description is kept in the key: pb200_prove on a
  * sharded key must be given the same slice and is collective over all ranks. */

@@ -33,11 +33,13 @@ class Pb200Error(RuntimeError):
 
 
 ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+DEV_COLLECTIVE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
 
 
 class Shard(ctypes.Structure):
     """`pb200_shard` (include/pb200.h)."""
-    _fields_ = [("rank", ctypes.c_uint32), ("world", ctypes.c_uint32), ("allgather", ALLGATHER_FN), ("user", ctypes.c_void_p)]
+    _fields_ = [("rank", ctypes.c_uint32), ("world", ctypes.c_uint32), ("allgather", ALLGATHER_FN), ("user", ctypes.c_void_p),
+                ("alltoall_dev", DEV_COLLECTIVE_FN), ("allgather_dev", DEV_COLLECTIVE_FN)]
 
 
 class Circuit(ctypes.Structure):
@@ -312,8 +314,9 @@ class Context:
     # -- PLONK prover rounds
     def preprocess(self, srs, selectors, wires, n_vars, label, shard=None):
         """selectors: 11 (n_gates, 4) uint64 arrays or None; wires: 4 uint32 arrays.  Returns (key handle, 15×48 vk bytes).
-        shard = (rank, world, allgather) makes the key point-range-sharded: `srs` is this rank's slice and
-        allgather(send: bytes) -> bytes of world × len(send), rank-major, is the host's collective."""
+        shard = (rank, world, allgather[, alltoall_dev, allgather_dev]) makes the key point-range-sharded: `srs` is this
+        rank's slice and allgather(send: bytes) -> bytes of world × len(send), rank-major, is the host's collective; the
+        two optional device collectives (send_ptr, recv_ptr, nbytes) -> None additionally shard round 3."""
         keep = []
         c = Circuit()
         c.n_gates = len(wires[0])
@@ -336,7 +339,19 @@ class Context:
         if shard is None:
             self._check(lib().pb200_preprocess(self._h, srs, ctypes.byref(c), bytes(label), len(label), ctypes.byref(h), _ptr(vk)))
             return h, vk.tobytes()
-        rank, world, gather = shard
+        rank, world, gather = shard[:3]
+        dev_fns = list(shard[3:5]) if len(shard) >= 5 else [None, None]
+
+        def dev_trampoline(fn):
+            def call(_user, send, recv, nbytes):
+                try:
+                    fn(send, recv, nbytes)
+                    return 0
+                except Exception:
+                    import traceback
+                    traceback.print_exc()
+                    return 2
+            return DEV_COLLECTIVE_FN(call)
 
         def trampoline(_user, send, recv, nbytes):
             try:
@@ -351,12 +366,13 @@ class Context:
                 return 2
 
         cb = ALLGATHER_FN(trampoline)
-        sh = Shard(rank, world, cb, None)
+        dev_cbs = [dev_trampoline(f) if f is not None else DEV_COLLECTIVE_FN() for f in dev_fns]
+        sh = Shard(rank, world, cb, None, dev_cbs[0], dev_cbs[1])
         self._check(lib().pb200_preprocess_sharded(self._h, srs, ctypes.byref(c), bytes(label), len(label), ctypes.byref(sh),
                                                    ctypes.byref(h), _ptr(vk)))
         if not hasattr(self, "_keepalive"):
             self._keepalive = {}
-        self._keepalive[h.value] = cb  # the key holds the function pointer for every later pb200_prove
+        self._keepalive[h.value] = (cb, dev_cbs)  # the key holds the function pointers for every later pb200_prove
         return h, vk.tobytes()
 
     def prover_key_free(self, pk):

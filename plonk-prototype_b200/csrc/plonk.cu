@@ -200,6 +200,11 @@ struct QuotArgs {
     const Fr *z, *pi, *l1;  // l1: L₁ on the coset (unscaled)
     Fr *out;
     uint32_t N4;
+    // Sharded round 3: w, z, pi and out are this rank's row-layout shards (`count` points, wire stride `count`), the
+    // shifted evaluations z(ωX), d(ωX) come from their own transforms (zw, dw) instead of index + 4, and local point
+    // e = r·m + k' is global point (row0 + r) + n1·k' of the key's natural-order vectors.  dist = 0: count = N4.
+    const Fr *zw, *dw;
+    uint32_t dist, count, log_m, log_n1, row0;
     Fr alpha, alpha2, beta, gamma, range_sep;
     Fr vh_inv[4];        // 1 / ((7ω_4n^i)^n − 1) has period 4 in i
     KFactors ks;
@@ -211,11 +216,13 @@ __device__ __forceinline__ Fr delta4(const Fr &f, const Fr &one) {  // f(f−1)(
 __device__ __forceinline__ Fr quad(const Fr &x) { return x.dbl().dbl(); }
 template <bool RANGE>
 __global__ void __launch_bounds__(128) quotient_kernel(const QuotArgs A) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.N4) return;
-    const uint32_t N4 = A.N4, inext = (i + 4) & (N4 - 1);
-    const Fr a = ld_fr(A.w + i), b = ld_fr(A.w + (size_t)N4 + i), c = ld_fr(A.w + 2 * (size_t)N4 + i),
-             d = ld_fr(A.w + 3 * (size_t)N4 + i);
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= A.count) return;
+    const uint32_t N4 = A.N4, ws = A.count;
+    const uint32_t i = A.dist ? (A.row0 + (e >> A.log_m)) + ((e & ((1u << A.log_m) - 1)) << A.log_n1) : e;
+    const uint32_t enext = (e + 4) & (N4 - 1);  // dist = 0 only
+    const Fr a = ld_fr(A.w + e), b = ld_fr(A.w + (size_t)ws + e), c = ld_fr(A.w + 2 * (size_t)ws + e),
+             d = ld_fr(A.w + 3 * (size_t)ws + e);
     // arithmetic widget
     Fr g = Fr::zero();
     if (A.q[Q_M]) g = (a * b) * ld_fr(A.q[Q_M] + i);
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(const QuotArgs A) {
     else g = Fr::zero();
     if (RANGE) {
         const Fr one = Fr::one();
-        const Fr dn = ld_fr(A.w + 3 * (size_t)N4 + inext);
+        const Fr dn = A.dist ? ld_fr(A.dw + e) : ld_fr(A.w + 3 * (size_t)ws + enext);
         const Fr kappa = A.range_sep.sqr();
         Fr r = delta4(dn - quad(a), one);
         r = r * kappa + delta4(a - quad(b), one);
@@ -236,9 +243,9 @@ __global__ void __launch_bounds__(128) quotient_kernel(const QuotArgs A) {
         r = r * kappa + delta4(c - quad(d), one);
         g = g + (r * A.range_sep) * ld_fr(A.q[Q_RANGE] + i);
     }
-    g = g + ld_fr(A.pi + i);
+    g = g + ld_fr(A.pi + e);
     // permutation: identity part, copy part, L1 part
-    const Fr zi = ld_fr(A.z + i), zn = ld_fr(A.z + inext);
+    const Fr zi = ld_fr(A.z + e), zn = A.dist ? ld_fr(A.zw + e) : ld_fr(A.z + enext);
     const Fr bx = A.beta * ld_fr(A.lin + i);
     const Fr ag = a + A.gamma, bg = b + A.gamma, cg = c + A.gamma, dg = d + A.gamma;
     Fr id = (ag + bx) * (bg + A.ks.k[1] * bx);
@@ -248,7 +255,38 @@ __global__ void __launch_bounds__(128) quotient_kernel(const QuotArgs A) {
     cp = cp * ((cg + A.beta * ld_fr(A.sig + 2 * (size_t)N4 + i)) * (dg + A.beta * ld_fr(A.sig + 3 * (size_t)N4 + i)));
     cp = cp * zn;
     Fr t = (id - cp) * A.alpha + ((zi - Fr::one()) * ld_fr(A.l1 + i)) * A.alpha2;
-    st_fr(A.out + i, (g + t) * A.vh_inv[i & 3]);
+    st_fr(A.out + e, (g + t) * A.vh_inv[i & 3]);
+}
+
+// Sharded round 3: this rank's column-layout shard A[j1][c] = x[j1·m + col0 + c] (n1 × cl) of the zero-padded, coset-scaled
+// polynomial x_j = p_j·gen^j (gen = 7, or 7ω for the evaluations of p(ωX)); four consecutive columns per thread.
+__global__ void __launch_bounds__(256) dist_load_kernel(Fr *dst, const Fr *poly, uint32_t n, uint32_t log_m, uint32_t log_cl, uint32_t col0,
+                                                        uint32_t local, Fr gen) {
+    const uint32_t e0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (e0 >= local) return;
+    const uint32_t j1 = e0 >> log_cl, c = e0 & ((1u << log_cl) - 1);
+    const uint32_t j0 = (j1 << log_m) + col0 + c;
+    Fr pw = j0 < n ? gen.pow_u32(j0) : Fr::zero();
+    for (uint32_t k = 0; k < 4; k++) {
+        const uint32_t j = j0 + k;
+        Fr v = Fr::zero();
+        if (j < n) {
+            v = ld_fr(poly + j) * pw;
+            pw = pw * gen;
+        }
+        st_fr(dst + e0 + k, v);
+    }
+}
+// … and back: t_j ← t_j·7^{−j} on the column-layout shard after the inverse transform
+__global__ void __launch_bounds__(256) dist_unscale_kernel(Fr *data, uint32_t log_m, uint32_t log_cl, uint32_t col0, uint32_t local, Fr gen_inv) {
+    const uint32_t e0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (e0 >= local) return;
+    const uint32_t j1 = e0 >> log_cl, c = e0 & ((1u << log_cl) - 1);
+    Fr pw = gen_inv.pow_u32((j1 << log_m) + col0 + c);
+    for (uint32_t k = 0; k < 4; k++) {
+        st_fr(data + e0 + k, ld_fr(data + e0 + k) * pw);
+        pw = pw * gen_inv;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ round 4 / 5
@@ -349,7 +387,7 @@ struct pb200_prover_key {
     uint8_t vk_bytes[15 * 48];
     merlin::Transcript *seeded = nullptr;
     // point-range sharding of the commitments (world = 1: none)
-    pb200_shard shard = {0, 1, nullptr, nullptr};
+    pb200_shard shard = {0, 1, nullptr, nullptr, nullptr, nullptr};
     size_t slice_lo = 0, slice_n = 0;  // this rank's coefficient range [slice_lo, slice_lo + slice_n)
 };
 
@@ -718,34 +756,98 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
         PB_LAUNCHED(ctx);
         PB_TRY(pb200_ntt_dev(ctx, (uint64_t *)pk->pi_poly, log_n, 1, 0));
     }
-    // coset evaluations on 4n: a, b, c, d | z | pi   (L₁ is kept from preprocessing)
-    Fr *w4 = pk->ev4, *z4 = pk->ev4 + 4 * N4, *pi4 = z4 + N4;
-    PB_TRY(coset_extend(ctx, w4, pk->w_poly, n32, log_n + 2, 4));
-    PB_TRY(coset_extend(ctx, z4, pk->z_poly, n32, log_n + 2, 1));
-    PB_TRY(coset_extend(ctx, pi4, pk->pi_poly, n32, log_n + 2, 1));
-    {
-        QuotArgs A;
-        for (int s = 0; s < kSel; s++) A.q[s] = pk->q_4n[s];
-        A.sig = pk->sig_4n;
-        A.lin = pk->lin_4n;
+    QuotArgs A;
+    for (int s = 0; s < kSel; s++) A.q[s] = pk->q_4n[s];
+    A.sig = pk->sig_4n;
+    A.lin = pk->lin_4n;
+    A.l1 = pk->l1_4n;
+    A.N4 = (uint32_t)N4;
+    A.alpha = to_dev(alpha);
+    A.alpha2 = to_dev(alpha.sqr());
+    A.beta = to_dev(beta);
+    A.gamma = to_dev(gamma);
+    A.range_sep = to_dev(range_sep);
+    for (int k = 0; k < 4; k++) A.vh_inv[k] = to_dev(pk->vh_inv[k]);
+    A.ks = ks;
+    A.zw = A.dw = nullptr;
+    A.dist = A.log_m = A.log_n1 = A.row0 = 0;
+    const bool range = pk->q_nonzero[Q_RANGE];
+    const uint32_t world = pk->shard.world, log_n4 = log_n + 2;
+    uint32_t log_g = 0;
+    while ((1u << log_g) < world) log_g++;
+    const bool dist3 = world > 1 && pk->shard.alltoall_dev && pk->shard.allgather_dev && log_n4 >= 8 + log_g + 2;
+    if (!dist3) {
+        // coset evaluations on 4n: a, b, c, d | z | pi   (L₁ is kept from preprocessing)
+        Fr *w4 = pk->ev4, *z4 = pk->ev4 + 4 * N4, *pi4 = z4 + N4;
+        PB_TRY(coset_extend(ctx, w4, pk->w_poly, n32, log_n4, 4));
+        PB_TRY(coset_extend(ctx, z4, pk->z_poly, n32, log_n4, 1));
+        PB_TRY(coset_extend(ctx, pi4, pk->pi_poly, n32, log_n4, 1));
         A.w = w4;
         A.z = z4;
         A.pi = pi4;
-        A.l1 = pk->l1_4n;
-        A.alpha2 = to_dev(alpha.sqr());
         A.out = pk->t_poly;
-        A.N4 = (uint32_t)N4;
-        A.alpha = to_dev(alpha);
-        A.beta = to_dev(beta);
-        A.gamma = to_dev(gamma);
-        A.range_sep = to_dev(range_sep);
-        for (int k = 0; k < 4; k++) A.vh_inv[k] = to_dev(pk->vh_inv[k]);
-        A.ks = ks;
-        if (pk->q_nonzero[Q_RANGE]) quotient_kernel<true><<<cdiv(N4, 128), 128, 0, st>>>(A);
+        A.count = (uint32_t)N4;
+        if (range) quotient_kernel<true><<<cdiv(N4, 128), 128, 0, st>>>(A);
         else quotient_kernel<false><<<cdiv(N4, 128), 128, 0, st>>>(A);
         PB_LAUNCHED(ctx);
+        PB_TRY(pb200_ntt_dev(ctx, (uint64_t *)pk->t_poly, log_n4, 1, 1));
+    } else {
+        // Sharded four-step transforms: N4 = n1 × m, this rank owns cl = m / world columns of the
+        // coefficient side and rl = n1 / world rows of the evaluation side; one all-to-all per transform.
+        const uint32_t log_n1 = 8, log_m = log_n4 - log_n1, log_cl = log_m - log_g, log_rl = log_n1 - log_g;
+        const uint32_t rank = pk->shard.rank, cl = 1u << log_cl, rl = 1u << log_rl, col0 = rank << log_cl;
+        const size_t local = N4 >> log_g, peer_bytes = (local >> log_g) * sizeof(Fr);
+        const HFr seven = HFr::from_u64(7);
+        Fr *shard = pk->ev4;                 // a b c d | z | pi | z(ωX) | d(ωX): 8 shards of `local` scalars
+        Fr *t_loc = pk->ev4 + 8 * local;     // this rank's quotient evaluations / coefficients
+        Fr *gathered = pk->ev4 + 9 * local;  // all ranks' coefficient shards (N4 scalars)
+        Fr *tmp = pk->t_poly;                // exchange buffer
+        struct { const Fr *poly; HFr gen; } src[8] = {{pk->w_poly, seven}, {pk->w_poly + n, seven}, {pk->w_poly + 2 * n, seven},
+                                                      {pk->w_poly + 3 * n, seven}, {pk->z_poly, seven}, {pk->pi_poly, seven},
+                                                      {pk->z_poly, seven * pk->omega}, {pk->w_poly + 3 * n, seven * pk->omega}};
+        const int n_src = range ? 8 : 7;
+        auto exchange = [&](Fr *send, Fr *recv) -> int {
+            PB_CUDA(ctx, cudaStreamSynchronize(st));
+            if (pk->shard.alltoall_dev(pk->shard.user, send, recv, peer_bytes) != 0)
+                return pb_fail(ctx, PB200_ERR_ARG, "sharded transform", "the all-to-all callback failed", __FILE__, __LINE__);
+            return 0;
+        };
+        for (int k = 0; k < n_src; k++) {
+            Fr *buf = shard + (size_t)k * local;
+            dist_load_kernel<<<cdiv(local / 4, 256), 256, 0, st>>>(buf, src[k].poly, n32, log_m, log_cl, col0, (uint32_t)local, to_dev(src[k].gen));
+            PB_LAUNCHED(ctx);
+            PB_TRY(pb200_ntt_columns_dev(ctx, (uint64_t *)buf, log_n4, log_n1, log_cl, col0, 0));
+            PB_TRY(exchange(buf, tmp));                                                              // block h (rl × cl) → rank h
+            PB_TRY(pb200_block_transpose_dev(ctx, (uint64_t *)buf, (const uint64_t *)tmp, world, rl, cl));  // → rl rows of length m
+        }
+        PB_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)shard, log_m, (uint32_t)n_src * rl, 0, 0));       // all rows of all shards at once
+        A.w = shard;
+        A.z = shard + 4 * local;
+        A.pi = shard + 5 * local;
+        A.zw = shard + 6 * local;
+        A.dw = shard + 7 * local;
+        A.out = t_loc;
+        A.dist = 1;
+        A.count = (uint32_t)local;
+        A.log_m = log_m;
+        A.log_n1 = log_n1;
+        A.row0 = rank << log_rl;
+        if (range) quotient_kernel<true><<<cdiv(local, 128), 128, 0, st>>>(A);
+        else quotient_kernel<false><<<cdiv(local, 128), 128, 0, st>>>(A);
+        PB_LAUNCHED(ctx);
+        // inverse: rows → regroup → all-to-all → columns (with n⁻¹ and the twiddles) → coset unscale
+        PB_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)t_loc, log_m, rl, 1, 0));
+        PB_TRY(pb200_block_transpose_dev(ctx, (uint64_t *)tmp, (const uint64_t *)t_loc, rl, world, cl));
+        PB_TRY(exchange(tmp, t_loc));
+        PB_TRY(pb200_ntt_columns_dev(ctx, (uint64_t *)t_loc, log_n4, log_n1, log_cl, col0, 1));
+        dist_unscale_kernel<<<cdiv(local / 4, 256), 256, 0, st>>>(t_loc, log_m, log_cl, col0, (uint32_t)local, to_dev(seven.inv()));
+        PB_LAUNCHED(ctx);
+        // every rank needs all of t(X) for rounds 4-5: all-gather the column shards, then back to natural order
+        PB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (pk->shard.allgather_dev(pk->shard.user, t_loc, gathered, local * sizeof(Fr)) != 0)
+            return pb_fail(ctx, PB200_ERR_ARG, "sharded transform", "the device all-gather callback failed", __FILE__, __LINE__);
+        PB_TRY(pb200_block_transpose_dev(ctx, (uint64_t *)pk->t_poly, (const uint64_t *)gathered, world, 1u << log_n1, cl));
     }
-    PB_TRY(pb200_ntt_dev(ctx, (uint64_t *)pk->t_poly, log_n + 2, 1, 1));
     const char *const t_label[4] = {"t_1", "t_2", "t_3", "t_4"};
     PB_TRY(commit_bytes_batch(ctx, srs, pk, pk->t_poly, n, 4, n, P + 48 * 5));
     for (int k = 0; k < 4; k++) tr.append_commitment(t_label[k], P + 48 * (5 + k));

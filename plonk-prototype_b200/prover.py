@@ -151,6 +151,30 @@ def torch_allgather(dist, device=None):
     return gather
 
 
+def torch_device_collectives(dist, device):
+    """(alltoall_dev, allgather_dev) for a sharded key: NCCL collectives on raw device pointers of the library's buffers,
+    wrapped as torch tensors through __cuda_array_interface__ (no copy).  Both return after the collective has completed."""
+    import torch
+
+    class _Dev:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+    def view(ptr, nbytes):
+        return torch.as_tensor(_Dev(ptr, nbytes), device=device)
+
+    def alltoall(send, recv, bytes_per_peer):
+        world = dist.get_world_size()
+        dist.all_to_all_single(view(recv, world * bytes_per_peer), view(send, world * bytes_per_peer))
+        torch.cuda.synchronize(device)
+
+    def allgather(send, recv, nbytes):
+        dist.all_gather_into_tensor(view(recv, dist.get_world_size() * nbytes), view(send, nbytes))
+        torch.cuda.synchronize(device)
+
+    return alltoall, allgather
+
+
 class ShardedParameters:
     """This rank's slice powers_of_g[rank·n/world .. (rank+1)·n/world) of `PublicParameters::setup(n − 1)`."""
 
