@@ -411,10 +411,15 @@ inline size_t eval_tiles(size_t n4) { return (n4 + kEvalTile - 1) / kEvalTile; }
 void carve(pb200_prover_key *pk, void *base, size_t *total) {
     Carver c(base);
     const size_t n = pk->n, N4 = 4 * n;
-    for (int s = 0; s < kSel; s++) {
+    // non-zero selectors back to back (coefficient forms, then coset evaluations) so that they transform and commit as a batch
+    size_t n_sel = 0;
+    for (int s = 0; s < kSel; s++) n_sel += pk->q_nonzero[s];
+    Fr *qp = c.take<Fr>(n_sel * n), *q4 = c.take<Fr>(n_sel * N4);
+    for (int s = 0, k = 0; s < kSel; s++) {
         if (!pk->q_nonzero[s]) continue;
-        pk->q_poly[s] = c.take<Fr>(n);
-        pk->q_4n[s] = c.take<Fr>(N4);
+        pk->q_poly[s] = qp ? qp + (size_t)k * n : nullptr;
+        pk->q_4n[s] = q4 ? q4 + (size_t)k * N4 : nullptr;
+        k++;
     }
     pk->sig_evals = c.take<Fr>(4 * n);
     pk->sig_poly = c.take<Fr>(4 * n);
@@ -645,18 +650,27 @@ extern "C" int pb200_preprocess_sharded(pb200_ctx *ctx, const pb200_srs *srs, co
 
     // selector and σ polynomials: interpolate, commit, extend to the 4n coset
     uint8_t *vk = pk->vk_bytes;
-    for (int s = 0; s < kSel; s++) {
-        uint8_t *dst = vk + 48 * s;
-        if (!pk->q_nonzero[s]) {
+    {
+        int first = -1;
+        uint32_t n_sel = 0;
+        for (int s = 0; s < kSel; s++) {
+            uint8_t *dst = vk + 48 * s;
             memset(dst, 0, 48);
             dst[0] = 0xc0;  // commitment to the zero polynomial: the identity
-            continue;
+            if (!pk->q_nonzero[s]) continue;
+            if (first < 0) first = s;
+            n_sel++;
+            PK_CUDA(cudaMemsetAsync(pk->q_poly[s], 0, n * sizeof(Fr), st));
+            PK_CUDA(cudaMemcpyAsync(pk->q_poly[s], circuit->selectors[s], ng * sizeof(Fr), cudaMemcpyHostToDevice, st));
         }
-        PK_CUDA(cudaMemsetAsync(pk->q_poly[s], 0, n * sizeof(Fr), st));
-        PK_CUDA(cudaMemcpyAsync(pk->q_poly[s], circuit->selectors[s], ng * sizeof(Fr), cudaMemcpyHostToDevice, st));
-        PK_TRY(pb200_ntt_dev(ctx, (uint64_t *)pk->q_poly[s], log_n, 1, 0));
-        PK_TRY(commit_bytes(ctx, srs, pk, pk->q_poly[s], n, dst));
-        PK_TRY(coset_extend(ctx, pk->q_4n[s], pk->q_poly[s], (uint32_t)n, log_n + 2, 1));
+        if (n_sel) {
+            uint8_t packed[kSel * 48];
+            PK_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)pk->q_poly[first], log_n, n_sel, 1, 0));
+            PK_TRY(commit_bytes_batch(ctx, srs, pk, pk->q_poly[first], n, n_sel, n, packed));
+            PK_TRY(coset_extend(ctx, pk->q_4n[first], pk->q_poly[first], (uint32_t)n, log_n + 2, n_sel));
+            for (int s = 0, k = 0; s < kSel; s++)
+                if (pk->q_nonzero[s]) memcpy(vk + 48 * s, packed + 48 * k++, 48);
+        }
     }
     PK_CUDA(cudaMemcpyAsync(pk->sig_poly, pk->sig_evals, 4 * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     PK_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)pk->sig_poly, log_n, 4, 1, 0));
