@@ -49,7 +49,7 @@ def main():
         ctx.prover_key_free(pk)
         sp.close()
         single_ms, matches = None, None
-        if rank == 0 and L <= 22:
+        if rank == 0 and L <= 24:
             pp = pb.PublicParameters(n - 1, tau, ctx)
             pk1, vk1 = ctx.preprocess(pp.srs, sel, wires, values.shape[0], label)
             p1 = ctx.prove(pp.srs, pk1, values, pi_pos, pi_vals)
