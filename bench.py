@@ -634,7 +634,7 @@ def bench_prove_sharded(ctx, dist, rank, world, local_rank, args):
         ctx.prover_key_free(pk)
         sp.close()
         out.append({"log_gates": L, "ms": sum(t) / len(t), "min_ms": min(t), "deterministic": len(proofs) == 1, "scaling": "strong"})
-    return {"metric": "sharded PLONK prove, %d GPUs (MSMs by point range + NCCL all-gather of partial commitments)" % world,
+    return {"metric": "sharded PLONK prove, %d GPUs (MSMs by point range + all-gather of partial commitments; round 3 as sharded four-step transforms)" % world,
             "unit": "ms", "sizes": out,
             "parity": "byte-identical with the single-GPU proof (scripts/dist_prove_check.py, profiles/dist_prove_*)"}
 

@@ -377,6 +377,7 @@ class Context:
 
     def prover_key_free(self, pk):
         lib().pb200_prover_key_free(self._h, pk)
+        getattr(self, "_keepalive", {}).pop(getattr(pk, "value", None), None)
 
     def prover_key_size(self, pk):
         return lib().pb200_prover_key_size(pk)
