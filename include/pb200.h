@@ -188,6 +188,10 @@ typedef int (*pb200_allgather_fn)(void *user, const void *send, void *recv, size
  * points, the quotient kernel and the inverse transform — is sharded too: four-step transforms with this rank owning a
  * column range of the coefficient side and a row range of the evaluation side (one all-to-all each, as in
  * pb200_ntt_columns_dev), the quotient evaluated on the local rows, and one all-gather of t(X)'s coefficient shards.
+ * With up to 8 ranks on one NVLink domain the forward exchange is not a collective at all: the keys' device memory is
+ * mapped into every peer with CUDA IPC (handles travel through `allgather`) and pb200_ntt_columns_scatter_dev stores each
+ * output straight into its owner's row buffer — transfer and transpose overlap the column arithmetic tile by tile; only the
+ * inverse transform and the final all-gather use the callbacks below.  Free sharded keys on all ranks together.
  * alltoall_dev: block h (bytes_per_peer bytes) of send_dev goes to rank h, block b of recv_dev comes from rank b.
  * allgather_dev: recv_dev = world × bytes, rank-major.  Both must have completed when they return. */
 typedef int (*pb200_alltoall_dev_fn)(void *user, const void *send_dev, void *recv_dev, size_t bytes_per_peer);

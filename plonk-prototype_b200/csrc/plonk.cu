@@ -15,7 +15,9 @@
 // Supported widgets: arithmetic and range (q_arith·(q_m·a·b + q_l·a + q_r·b + q_o·c + q_4·d + q_c) + PI and the
 // q_range quad check).  A circuit with non-zero q_logic / q_fixed_group_add / q_variable_group_add columns is
 // rejected with PB200_ERR_ARG — there is no silent fallback.
+#include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -389,6 +391,9 @@ struct pb200_prover_key {
     // point-range sharding of the commitments (world = 1: none)
     pb200_shard shard = {0, 1, nullptr, nullptr, nullptr, nullptr};
     size_t slice_lo = 0, slice_n = 0;  // this rank's coefficient range [slice_lo, slice_lo + slice_n)
+    // peer mappings of every rank's key slab (CUDA IPC over NVLink) for the fused column-transform + exchange kernel
+    void *peer_slab[8] = {};
+    bool peers_open = false, peers_failed = false;
 };
 
 namespace {
@@ -433,7 +438,10 @@ void carve(pb200_prover_key *pk, void *base, size_t *total) {
     pk->w_poly = c.take<Fr>(4 * n);
     pk->z_poly = c.take<Fr>(n);
     pk->pi_poly = c.take<Fr>(n);
-    pk->ev4 = c.take<Fr>(6 * N4);  // a, b, c, d | z | pi on the coset
+    // a, b, c, d | z | pi on the coset; a sharded key holds 8 column shards, 8 row buffers, the local quotient and the
+    // gathered coefficients of t(X) here instead
+    const size_t world = pk->shard.world;
+    pk->ev4 = c.take<Fr>(std::max<size_t>(6 * N4, world > 1 ? 17 * (N4 / world) + N4 + 64 : 0));
     pk->t_poly = c.take<Fr>(N4);
     pk->lin_poly = c.take<Fr>(n);
     pk->agg = c.take<Fr>(n);
@@ -510,6 +518,8 @@ struct RoundClock {
 extern "C" void pb200_prover_key_free(pb200_ctx *ctx, pb200_prover_key *pk) {
     if (!pk) return;
     if (ctx) cudaSetDevice(ctx->device);
+    for (uint32_t h = 0; h < 8; h++)
+        if (pk->peer_slab[h] && h != pk->shard.rank) cudaIpcCloseMemHandle(pk->peer_slab[h]);
     cudaFree(pk->slab);
     cudaFree(pk->pi_pos);
     delete pk->seeded;
@@ -812,10 +822,11 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
         const uint32_t rank = pk->shard.rank, cl = 1u << log_cl, rl = 1u << log_rl, col0 = rank << log_cl;
         const size_t local = N4 >> log_g, peer_bytes = (local >> log_g) * sizeof(Fr);
         const HFr seven = HFr::from_u64(7);
-        Fr *shard = pk->ev4;                 // a b c d | z | pi | z(ωX) | d(ωX): 8 shards of `local` scalars
-        Fr *t_loc = pk->ev4 + 8 * local;     // this rank's quotient evaluations / coefficients
-        Fr *gathered = pk->ev4 + 9 * local;  // all ranks' coefficient shards (N4 scalars)
-        Fr *tmp = pk->t_poly;                // exchange buffer
+        Fr *cols = pk->ev4;                   // column-layout shards (sources of the fused kernel): 8 × `local` scalars
+        Fr *shard = pk->ev4 + 8 * local;      // row-layout shards a b c d | z | pi | z(ωX) | d(ωX)
+        Fr *t_loc = pk->ev4 + 16 * local;     // this rank's quotient evaluations / coefficients
+        Fr *gathered = pk->ev4 + 17 * local;  // all ranks' coefficient shards (N4 scalars)
+        Fr *tmp = pk->t_poly;                 // exchange buffer of the NCCL path
         struct { const Fr *poly; HFr gen; } src[8] = {{pk->w_poly, seven}, {pk->w_poly + n, seven}, {pk->w_poly + 2 * n, seven},
                                                       {pk->w_poly + 3 * n, seven}, {pk->z_poly, seven}, {pk->pi_poly, seven},
                                                       {pk->z_poly, seven * pk->omega}, {pk->w_poly + 3 * n, seven * pk->omega}};
@@ -826,14 +837,56 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
                 return pb_fail(ctx, PB200_ERR_ARG, "sharded transform", "the all-to-all callback failed", __FILE__, __LINE__);
             return 0;
         };
-        for (int k = 0; k < n_src; k++) {
-            Fr *buf = shard + (size_t)k * local;
-            dist_load_kernel<<<cdiv(local / 4, 256), 256, 0, st>>>(buf, src[k].poly, n32, log_m, log_cl, col0, (uint32_t)local, to_dev(src[k].gen));
-            PB_LAUNCHED(ctx);
-            PB_TRY(pb200_ntt_columns_dev(ctx, (uint64_t *)buf, log_n4, log_n1, log_cl, col0, 0));
-            PB_TRY(exchange(buf, tmp));                                                              // block h (rl × cl) → rank h
-            PB_TRY(pb200_block_transpose_dev(ctx, (uint64_t *)buf, (const uint64_t *)tmp, world, rl, cl));  // → rl rows of length m
+        auto barrier = [&]() -> int {  // every rank's stream has drained: a one-byte all-gather through the host collective
+            PB_CUDA(ctx, cudaStreamSynchronize(st));
+            uint8_t one_byte = 1, all[8];
+            if (pk->shard.allgather(pk->shard.user, &one_byte, all, 1) != 0)
+                return pb_fail(ctx, PB200_ERR_ARG, "sharded transform", "the all-gather callback failed", __FILE__, __LINE__);
+            return 0;
+        };
+        // Peer mappings of all key slabs, once per key: the forward exchange is then the column kernel's own store
+        // (pb200_ntt_columns_scatter_dev writes every output into the owner's row buffer over NVLink).  The keys have the
+        // same layout on every rank (same circuit), so a peer's buffer is its slab base plus this rank's offset.
+        static const bool force_nccl = getenv("PB200_ROUND3_NCCL") != nullptr;  // measurement switch
+        if (!pk->peers_open && !pk->peers_failed && !force_nccl && world <= 8) {
+            cudaIpcMemHandle_t mine;
+            std::vector<cudaIpcMemHandle_t> all(world);
+            bool ok = cudaIpcGetMemHandle(&mine, pk->slab) == cudaSuccess;
+            uint8_t flag = ok ? 1 : 0;
+            if (!ok) memset(&mine, 0, sizeof(mine));
+            if (pk->shard.allgather(pk->shard.user, &mine, all.data(), sizeof(mine)) != 0)
+                return pb_fail(ctx, PB200_ERR_ARG, "sharded transform", "the all-gather callback failed", __FILE__, __LINE__);
+            for (uint32_t h = 0; h < world && ok; h++) {
+                if (h == rank) pk->peer_slab[h] = pk->slab;
+                else ok = cudaIpcOpenMemHandle(&pk->peer_slab[h], all[h], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+            }
+            flag = ok ? 1 : 0;
+            uint8_t flags[8];
+            if (pk->shard.allgather(pk->shard.user, &flag, flags, 1) != 0)
+                return pb_fail(ctx, PB200_ERR_ARG, "sharded transform", "the all-gather callback failed", __FILE__, __LINE__);
+            for (uint32_t h = 0; h < world; h++) ok = ok && flags[h];
+            (void)cudaGetLastError();
+            pk->peers_open = ok;        // all ranks or none: otherwise fall back to the NCCL all-to-all everywhere
+            pk->peers_failed = !ok;
         }
+        const bool fused = pk->peers_open && !force_nccl;
+        if (fused) PB_TRY(barrier());  // nobody is still reading the row buffers of an earlier use
+        for (int k = 0; k < n_src; k++) {
+            Fr *col = cols + (size_t)k * local, *row = shard + (size_t)k * local;
+            dist_load_kernel<<<cdiv(local / 4, 256), 256, 0, st>>>(col, src[k].poly, n32, log_m, log_cl, col0, (uint32_t)local, to_dev(src[k].gen));
+            PB_LAUNCHED(ctx);
+            if (fused) {
+                void *peer_rows[8];
+                const size_t off = (size_t)((char *)row - (char *)pk->slab);
+                for (uint32_t h = 0; h < world; h++) peer_rows[h] = (char *)pk->peer_slab[h] + off;
+                PB_TRY(pb200_ntt_columns_scatter_dev(ctx, (uint64_t *)col, log_n4, log_n1, log_cl, col0, world, peer_rows));
+            } else {
+                PB_TRY(pb200_ntt_columns_dev(ctx, (uint64_t *)col, log_n4, log_n1, log_cl, col0, 0));
+                PB_TRY(exchange(col, tmp));                                                              // block h (rl × cl) → rank h
+                PB_TRY(pb200_block_transpose_dev(ctx, (uint64_t *)row, (const uint64_t *)tmp, world, rl, cl));  // → rl rows of length m
+            }
+        }
+        if (fused) PB_TRY(barrier());  // every rank has finished storing into every row buffer
         PB_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)shard, log_m, (uint32_t)n_src * rl, 0, 0));       // all rows of all shards at once
         A.w = shard;
         A.z = shard + 4 * local;
