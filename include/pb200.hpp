@@ -1,0 +1,342 @@
+// pb200.hpp — header-only C++ host layer over the C ABI (pb200.h), shaped like the Rust API the reference is written
+// against, for hosts that cannot use the Rust crates (this image has no cargo / rustc; INTEGRATION.md shows the Rust shim).
+//
+// Names, argument meaning and error behaviour follow dusk-plonk 0.8.2 / dusk-bls12_381 0.8 (pinned at
+// /root/reference/Cargo.toml:19-20):
+//   BlsScalar                          dusk_bls12_381::BlsScalar (Montgomery limbs; +, −, *, neg, invert, pow, from(u64))
+//   EvaluationDomain::{new_, fft, ifft, coset_fft, coset_ifft}     dusk_plonk::fft::EvaluationDomain
+//   msm_variable_base(points, scalars) dusk_bls12_381::multiscalar_mul::msm_variable_base
+//   PublicParameters::setup, CommitKey::commit                     dusk_plonk::commitment_scheme::kzg10
+//   StandardComposer::{add_input, add, mul, mul_gate, boolean_gate, constrain_to_constant,
+//                      add_witness_to_circuit_description}          the calls /root/reference/src/zk/gadgets.rs makes
+//   Prover::{new_, mut_cs, preprocess, prove}, verify_proof         dusk_plonk::proof_system
+// Upstream's infallible functions stay infallible here: a backend failure throws pb200::Error (the Rust shim panics) —
+// there is no CPU fallback.  `EvaluationDomain::new_` throws InvalidEvalDomainSize for log2(size) ≥ 32 like upstream's Err.
+#pragma once
+#include <array>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../plonk-prototype_b200/csrc/host_field.h"
+#include "pb200.h"
+
+namespace pb200 {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct InvalidEvalDomainSize : Error {
+    using Error::Error;
+};
+
+// ---- BlsScalar ------------------------------------------------------------------------------------------------
+struct BlsScalar {
+    hostf::HFr v;  // Montgomery form, fully reduced: the memory image of `BlsScalar.0`
+    BlsScalar() : v(hostf::HFr::zero()) {}
+    explicit BlsScalar(const hostf::HFr &x) : v(x) {}
+    static BlsScalar zero() { return BlsScalar(); }
+    static BlsScalar one() { return BlsScalar(hostf::HFr::one()); }
+    static BlsScalar from(uint64_t x) { return BlsScalar(hostf::HFr::from_u64(x)); }
+    static BlsScalar pow_of_2(uint64_t k) { return from(2).pow(k); }
+    BlsScalar operator+(const BlsScalar &o) const { return BlsScalar(v + o.v); }
+    BlsScalar operator-(const BlsScalar &o) const { return BlsScalar(v - o.v); }
+    BlsScalar operator*(const BlsScalar &o) const { return BlsScalar(v * o.v); }
+    BlsScalar operator-() const { return BlsScalar(v.neg()); }
+    bool operator==(const BlsScalar &o) const { return v == o.v; }
+    bool operator!=(const BlsScalar &o) const { return v != o.v; }
+    BlsScalar pow(uint64_t e) const { return BlsScalar(v.pow_u64(e)); }
+    // `invert()`: (is_some, value) — zero has no inverse
+    std::pair<bool, BlsScalar> invert() const { return {!v.is_zero(), BlsScalar(v.inv())}; }
+    // `reduce()`: Montgomery → canonical limbs kept in the same struct (what bits_count / divn work on)
+    std::array<uint64_t, 4> reduce() const {
+        const hostf::HFr c = v.from_mont();
+        return {c.l[0], c.l[1], c.l[2], c.l[3]};
+    }
+    std::array<uint8_t, 32> to_bytes() const {
+        std::array<uint8_t, 32> b;
+        hostf::fr_to_bytes(v, b.data());
+        return b;
+    }
+};
+static_assert(sizeof(BlsScalar) == 32, "BlsScalar is 4 × u64");
+
+// ---- context ---------------------------------------------------------------------------------------------------
+class Context {
+  public:
+    explicit Context(int device = 0) {
+        if (pb200_init(&ctx_, device) != 0) {
+            std::string msg = ctx_ ? pb200_last_error(ctx_) : "no usable sm_100 GPU";
+            if (ctx_) pb200_destroy(ctx_);
+            ctx_ = nullptr;
+            throw Error("pb200_init failed: " + msg + " — there is no CPU fallback");
+        }
+    }
+    ~Context() {
+        if (ctx_) pb200_destroy(ctx_);
+    }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    pb200_ctx *raw() const { return ctx_; }
+    void check(int rc, const char *what) const {
+        if (rc != 0) throw Error(std::string(what) + ": " + pb200_last_error(ctx_));
+    }
+
+  private:
+    pb200_ctx *ctx_ = nullptr;
+};
+
+// ---- EvaluationDomain ------------------------------------------------------------------------------------------
+class EvaluationDomain {
+  public:
+    static EvaluationDomain new_(Context &ctx, size_t num_coeffs) {
+        uint32_t log_n = 0;
+        if (pb200_domain_log_size(num_coeffs, &log_n) != 0) throw InvalidEvalDomainSize("log2(size) >= 32");
+        return EvaluationDomain(ctx, log_n);
+    }
+    size_t size() const { return (size_t)1 << log_n_; }
+    uint32_t log_size_of_group() const { return log_n_; }
+    std::vector<BlsScalar> fft(const std::vector<BlsScalar> &coeffs) const { return run(coeffs, 0, 0); }
+    std::vector<BlsScalar> ifft(const std::vector<BlsScalar> &evals) const { return run(evals, 1, 0); }
+    std::vector<BlsScalar> coset_fft(const std::vector<BlsScalar> &coeffs) const { return run(coeffs, 0, 1); }
+    std::vector<BlsScalar> coset_ifft(const std::vector<BlsScalar> &evals) const { return run(evals, 1, 1); }
+
+  private:
+    EvaluationDomain(Context &ctx, uint32_t log_n) : ctx_(&ctx), log_n_(log_n) {}
+    std::vector<BlsScalar> run(std::vector<BlsScalar> v, int inverse, int coset) const {
+        if (v.size() > size()) throw Error("more coefficients than the domain holds");
+        v.resize(size());  // upstream zero-pads
+        ctx_->check(pb200_ntt(ctx_->raw(), reinterpret_cast<uint64_t *>(v.data()), log_n_, inverse, coset), "pb200_ntt");
+        return v;
+    }
+    Context *ctx_;
+    uint32_t log_n_;
+};
+
+// ---- G1 / MSM / KZG --------------------------------------------------------------------------------------------
+struct G1Affine {
+    uint64_t x[6], y[6];  // Montgomery; the identity is not representable (an SRS never holds it)
+};
+struct G1Projective {
+    uint64_t xyz[18];  // X ‖ Y ‖ Z, not normalised (as upstream's msm_variable_base returns it)
+    bool is_identity() const {
+        uint64_t o = 0;
+        for (int i = 12; i < 18; i++) o |= xyz[i];
+        return o == 0;
+    }
+    // G1Affine::from(self).to_bytes(): 48-byte compressed encoding
+    std::array<uint8_t, 48> to_bytes() const {
+        std::array<uint8_t, 48> b;
+        hostf::g1_projective_to_bytes(xyz, b.data());
+        return b;
+    }
+};
+static_assert(sizeof(G1Affine) == 96, "packed affine point");
+
+class CommitKey {
+  public:
+    // CommitKey { powers_of_g }: uploaded once, resident; pre-doubled window copies for prover-size keys
+    CommitKey(Context &ctx, const std::vector<G1Affine> &powers_of_g) : ctx_(&ctx) {
+        ctx.check(pb200_srs_upload(ctx.raw(), reinterpret_cast<const uint64_t *>(powers_of_g.data()), powers_of_g.size(), &srs_), "pb200_srs_upload");
+        if (powers_of_g.size() <= ((size_t)1 << 22)) ctx.check(pb200_srs_precompute(ctx.raw(), srs_), "pb200_srs_precompute");
+    }
+    // PublicParameters::setup(max_degree, rng) with the trapdoor supplied by the caller (test / benchmark parameters)
+    static CommitKey setup(Context &ctx, size_t max_degree, const BlsScalar &tau) {
+        pb200_srs *srs = nullptr;
+        ctx.check(pb200_srs_generate(ctx.raw(), tau.v.l, max_degree + 1, &srs), "pb200_srs_generate");
+        if (max_degree + 1 <= ((size_t)1 << 22)) ctx.check(pb200_srs_precompute(ctx.raw(), srs), "pb200_srs_precompute");
+        return CommitKey(ctx, srs);
+    }
+    CommitKey(CommitKey &&o) noexcept : ctx_(o.ctx_), srs_(o.srs_) { o.srs_ = nullptr; }
+    CommitKey(const CommitKey &) = delete;
+    ~CommitKey() {
+        if (srs_) pb200_srs_free(ctx_->raw(), srs_);
+    }
+    size_t max_degree() const { return pb200_srs_len(srs_) - 1; }
+    // commit(&Polynomial): degree check, then one MSM over powers_of_g[..len]
+    G1Projective commit(const std::vector<BlsScalar> &coeffs) const {
+        if (coeffs.size() > pb200_srs_len(srs_)) throw Error("PolynomialDegreeTooLarge");
+        G1Projective out;
+        ctx_->check(pb200_msm_g1(ctx_->raw(), srs_, 0, reinterpret_cast<const uint64_t *>(coeffs.data()), coeffs.size(), out.xyz), "pb200_msm_g1");
+        return out;
+    }
+    pb200_srs *raw() const { return srs_; }
+
+  private:
+    CommitKey(Context &ctx, pb200_srs *srs) : ctx_(&ctx), srs_(srs) {}
+    Context *ctx_;
+    pb200_srs *srs_ = nullptr;
+};
+
+// msm_variable_base(points, scalars): infallible like upstream (a backend failure throws), empty input ⇒ identity.
+inline G1Projective msm_variable_base(Context &ctx, const std::vector<G1Affine> &points, const std::vector<BlsScalar> &scalars) {
+    if (points.size() != scalars.size()) throw Error("points and scalars differ in length");
+    G1Projective out;
+    if (points.empty()) {
+        ctx.check(pb200_msm_g1(ctx.raw(), nullptr, 0, nullptr, 0, out.xyz), "pb200_msm_g1");
+        return out;
+    }
+    pb200_srs *srs = nullptr;
+    ctx.check(pb200_srs_upload(ctx.raw(), reinterpret_cast<const uint64_t *>(points.data()), points.size(), &srs), "pb200_srs_upload");
+    const int rc = pb200_msm_g1(ctx.raw(), srs, 0, reinterpret_cast<const uint64_t *>(scalars.data()), scalars.size(), out.xyz);
+    pb200_srs_free(ctx.raw(), srs);
+    ctx.check(rc, "pb200_msm_g1");
+    return out;
+}
+
+// ---- StandardComposer ------------------------------------------------------------------------------------------
+typedef uint32_t Variable;
+
+class StandardComposer {
+  public:
+    StandardComposer() {
+        zero_var_ = 0;
+        zero_var_ = add_witness_to_circuit_description(BlsScalar::zero());
+        add_dummy_constraints();
+    }
+    size_t circuit_size() const { return w_[0].size(); }
+    Variable zero_var() const { return zero_var_; }
+    const BlsScalar &value_of(Variable v) const { return variables_[v]; }
+
+    Variable add_input(const BlsScalar &s) {
+        variables_.push_back(s);
+        return (Variable)(variables_.size() - 1);
+    }
+    // c = q_l·a + q_r·b + q_c + pi, constrained with q_o = −1
+    Variable add(std::pair<BlsScalar, Variable> q_l_a, std::pair<BlsScalar, Variable> q_r_b, const BlsScalar &q_c, const BlsScalar *pi = nullptr) {
+        BlsScalar c = q_l_a.first * variables_[q_l_a.second] + q_r_b.first * variables_[q_r_b.second] + q_c;
+        if (pi) c = c + *pi;
+        const Variable out = add_input(c);
+        row(q_l_a.second, q_r_b.second, out, zero_var_, BlsScalar::zero(), q_l_a.first, q_r_b.first, -BlsScalar::one(), q_c, pi);
+        return out;
+    }
+    // c = q_m·a·b + q_c + pi, constrained with q_o = −1
+    Variable mul(const BlsScalar &q_m, Variable a, Variable b, const BlsScalar &q_c, const BlsScalar *pi = nullptr) {
+        BlsScalar c = q_m * variables_[a] * variables_[b] + q_c;
+        if (pi) c = c + *pi;
+        const Variable out = add_input(c);
+        row(a, b, out, zero_var_, q_m, BlsScalar::zero(), BlsScalar::zero(), -BlsScalar::one(), q_c, pi);
+        return out;
+    }
+    void mul_gate(Variable a, Variable b, Variable c, const BlsScalar &q_m, const BlsScalar &q_o, const BlsScalar &q_c, const BlsScalar *pi = nullptr) {
+        row(a, b, c, zero_var_, q_m, BlsScalar::zero(), BlsScalar::zero(), q_o, q_c, pi);
+    }
+    void add_gate(Variable a, Variable b, Variable c, const BlsScalar &q_l, const BlsScalar &q_r, const BlsScalar &q_o, const BlsScalar &q_c,
+                  const BlsScalar *pi = nullptr) {
+        row(a, b, c, zero_var_, BlsScalar::zero(), q_l, q_r, q_o, q_c, pi);
+    }
+    void boolean_gate(Variable a) {
+        row(a, a, a, zero_var_, BlsScalar::one(), BlsScalar::zero(), BlsScalar::zero(), -BlsScalar::one(), BlsScalar::zero(), nullptr);
+    }
+    void constrain_to_constant(Variable a, const BlsScalar &constant, const BlsScalar *pi = nullptr) {
+        row(a, a, a, zero_var_, BlsScalar::zero(), BlsScalar::one(), BlsScalar::zero(), BlsScalar::zero(), -constant, pi);
+    }
+    Variable add_witness_to_circuit_description(const BlsScalar &value) {
+        const Variable v = add_input(value);
+        constrain_to_constant(v, value, nullptr);
+        return v;
+    }
+
+    // column images for pb200_preprocess / pb200_prove
+    pb200_circuit circuit() const {
+        pb200_circuit c;
+        c.n_gates = circuit_size();
+        c.n_vars = variables_.size();
+        for (int k = 0; k < 11; k++) c.selectors[k] = k < 7 ? reinterpret_cast<const uint64_t *>(q_[k].data()) : nullptr;
+        for (int k = 0; k < 4; k++) c.wires[k] = w_[k].data();
+        return c;
+    }
+    const std::vector<BlsScalar> &variables() const { return variables_; }
+    const std::map<uint32_t, BlsScalar> &public_inputs_sparse_store() const { return pi_; }
+
+  private:
+    enum { QM, QL, QR, QO, QC, Q4, QARITH };
+    void row(Variable a, Variable b, Variable c, Variable d, const BlsScalar &q_m, const BlsScalar &q_l, const BlsScalar &q_r,
+             const BlsScalar &q_o, const BlsScalar &q_c, const BlsScalar *pi, const BlsScalar &q_4 = BlsScalar::zero()) {
+        const BlsScalar vals[7] = {q_m, q_l, q_r, q_o, q_c, q_4, BlsScalar::one()};
+        for (int k = 0; k < 7; k++) q_[k].push_back(vals[k]);
+        const Variable w[4] = {a, b, c, d};
+        for (int k = 0; k < 4; k++) w_[k].push_back(w[k]);
+        if (pi) pi_[(uint32_t)(w_[0].size() - 1)] = *pi;
+    }
+    void add_dummy_constraints() {
+        const Variable six = add_input(BlsScalar::from(6)), one = add_input(BlsScalar::one()), seven = add_input(BlsScalar::from(7)),
+                       m20 = add_input(-BlsScalar::from(20));
+        row(six, seven, m20, one, BlsScalar::one(), BlsScalar::from(2), BlsScalar::from(3), BlsScalar::from(4), BlsScalar::from(4), nullptr,
+            BlsScalar::one());
+        row(m20, six, seven, zero_var_, BlsScalar::one(), BlsScalar::one(), BlsScalar::one(), BlsScalar::one(), BlsScalar::from(127), nullptr);
+    }
+    std::vector<BlsScalar> q_[7];
+    std::vector<Variable> w_[4];
+    std::vector<BlsScalar> variables_;
+    std::map<uint32_t, BlsScalar> pi_;
+    Variable zero_var_;
+};
+
+// ---- Prover / verify --------------------------------------------------------------------------------------------
+typedef std::array<uint8_t, 1040> ProofBytes;
+typedef std::array<uint8_t, 15 * 48> VerifierKeyBytes;
+
+class Prover {
+  public:
+    static Prover new_(Context &ctx, const std::string &label) { return Prover(ctx, label); }
+    Prover(Prover &&o) noexcept : ctx_(o.ctx_), label_(std::move(o.label_)), cs_(std::move(o.cs_)), key_(o.key_), vk_(o.vk_) { o.key_ = nullptr; }
+    Prover(const Prover &) = delete;
+    ~Prover() {
+        if (key_) pb200_prover_key_free(ctx_->raw(), key_);
+    }
+    StandardComposer &mut_cs() { return cs_; }
+    size_t circuit_size() const { return cs_.circuit_size(); }
+    size_t padded_size() const { return pb200_prover_key_size(key_); }
+    const VerifierKeyBytes &verifier_key() const { return vk_; }
+    void preprocess(const CommitKey &ck) {
+        if (key_) throw Error("CircuitAlreadyPreprocessed");
+        const pb200_circuit c = cs_.circuit();
+        ctx_->check(pb200_preprocess(ctx_->raw(), ck.raw(), &c, reinterpret_cast<const uint8_t *>(label_.data()), label_.size(), &key_, vk_.data()),
+                    "pb200_preprocess");
+    }
+    ProofBytes prove(const CommitKey &ck) {
+        if (!key_) preprocess(ck);
+        std::vector<uint32_t> pos;
+        std::vector<BlsScalar> val;
+        for (const auto &kv : cs_.public_inputs_sparse_store()) {
+            pos.push_back(kv.first);
+            val.push_back(kv.second);
+        }
+        ProofBytes proof;
+        ctx_->check(pb200_prove(ctx_->raw(), ck.raw(), key_, reinterpret_cast<const uint64_t *>(cs_.variables().data()), pos.data(),
+                                reinterpret_cast<const uint64_t *>(val.data()), pos.size(), proof.data()),
+                    "pb200_prove");
+        return proof;
+    }
+
+  private:
+    Prover(Context &ctx, const std::string &label) : ctx_(&ctx), label_(label) {}
+    Context *ctx_;
+    std::string label_;
+    StandardComposer cs_;
+    pb200_prover_key *key_ = nullptr;
+    VerifierKeyBytes vk_{};
+};
+
+// circuit::verify_proof: host CPU (pairing), independent of the circuit size.  tau is the trapdoor of the test parameters.
+inline bool verify_proof(const VerifierKeyBytes &vk, size_t padded_size, const std::string &label, const ProofBytes &proof,
+                         const std::map<uint32_t, BlsScalar> &public_inputs, const BlsScalar &tau) {
+    uint64_t beta_h[24];
+    if (pb200_opening_key_from_tau(tau.v.l, beta_h) != 0) throw Error("pb200_opening_key_from_tau");
+    std::vector<uint32_t> pos;
+    std::vector<BlsScalar> val;
+    for (const auto &kv : public_inputs) {
+        pos.push_back(kv.first);
+        val.push_back(kv.second);
+    }
+    int accepted = 0;
+    if (pb200_verify(vk.data(), padded_size, reinterpret_cast<const uint8_t *>(label.data()), label.size(), proof.data(), pos.data(),
+                     reinterpret_cast<const uint64_t *>(val.data()), pos.size(), beta_h, &accepted) != 0)
+        throw Error("pb200_verify: bad argument");
+    return accepted != 0;
+}
+
+}  // namespace pb200

@@ -60,3 +60,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp", "Makefile")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(text), os.path.join(dirpath, f)
+
+
+def test_cxx_host_layer_example_builds_and_refuses_to_run_without_gpu():
+    """include/pb200.hpp + examples/mock_circuit.cpp (the reference's valid_balance circuit through the C++ host layer):
+    compiles and links against libpb200.so; without a GPU it must fail loudly, not fall back."""
+    import subprocess
+    import torch
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "plonk-prototype_b200", "csrc"), "-s", "example"])
+    exe = os.path.join(ROOT, "examples", "mock_circuit")
+    assert os.path.exists(exe)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present (the gpu-marked test runs it)")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr

@@ -272,6 +272,19 @@ def test_reference_mock_circuit_valid_balance_proves_and_verifies(ctx):
     pp.close()
 
 
+def test_cxx_host_layer_example_runs(ctx):
+    """examples/mock_circuit.cpp: MockCircuit::valid_balance built with pb200::StandardComposer, proved, verified, tampering
+    rejected, EvaluationDomain round trip, KZG commits — all through include/pb200.hpp."""
+    import subprocess
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    exe = os.path.join(root, "examples", "mock_circuit")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(root, "plonk-prototype_b200", "csrc"), "-s", "example"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "proof verified" in r.stdout
+
+
 def test_unsupported_widget_is_rejected_loudly(ctx):
     import plonk_prototype_b200 as pb
     comp = pm.synthetic_circuit(13)
