@@ -70,7 +70,7 @@ int main() {
         CHECK(cs.value_of(out) == BlsScalar::one());
         const BlsScalar minus_one = -BlsScalar::one();
         cs.constrain_to_constant(out, BlsScalar::zero(), &minus_one);  // expose the 0/1 result as a public input
-        CommitKey ck = CommitKey::setup(ctx, cs.circuit_size() + 64, tau);
+        CommitKey ck = CommitKey::setup(ctx, 1023, tau);  // PublicParameters::setup(max_degree): covers the circuit and the commits below
         prover.preprocess(ck);
         const ProofBytes proof = prover.prove(ck);
         CHECK(proof == prover.prove(ck));  // deterministic (no blinding in 0.8.x)
