@@ -599,8 +599,14 @@ def bench_prove(ctx, stream, args, with_cpu=True):
         gpu_same = None
         if cl != L:
             gpu_same = gpu_prove_ms(ctx, cl)
+        # what /root/reference/Cargo.toml:19 actually builds (default-features = false: no rayon) is single-threaded:
+        # timed at 2^14 gates (≈ 8 s), with the GPU prove of the same circuit beside it
+        _, t_prove_1 = cpu_prove_sample(14, 1)
+        gpu_14 = gpu_prove_ms(ctx, 14)
         out["cpu_baseline"] = {"value": 1e3 * t_prove, "unit": "ms", "cores": cores, "kind": "port", "log_gates": cl,
                                "preprocess_ms": 1e3 * t_pre, "gpu_ms_same_size": gpu_same,
+                               "single_thread": {"log_gates": 14, "cpu_ms": 1e3 * t_prove_1, "gpu_ms": gpu_14,
+                                                 "note": "1 thread = the reference's own feature set (no rayon)"},
                                "sample": "C restatement of dusk-plonk 0.8 prove_with_preprocessed (oracle/plonk_oracle.inc: same NTT/MSM "
                                          "call list, window-parallel MSM and parallel FFT/quotient loop as the rayon build) on the "
                                          "same synthetic circuit at 2^%d gates, %d threads; Rust reference not buildable here" % (cl, cores)}
