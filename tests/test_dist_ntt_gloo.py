@@ -116,3 +116,24 @@ def test_layout_maps_are_consistent():
         for i in (0, 1, 63, 64, 517, spec.n - 1):
             g, off = fn(i)
             assert (shards[g][off] == v[i]).all(), (layout, i)
+
+
+def test_sharded_round3_index_formulas_match_shard_spec():
+    """csrc/plonk.cu's sharded round 3 addresses its shards with closed formulas — column shard element e = j1·cl + c holds
+    coefficient j1·m + rank·cl + c (dist_load_kernel), row shard element e = r·m + k' is evaluation point
+    (rank·rl + r) + n1·k' (quotient_kernel, dist = 1).  They must be the maps of ShardSpec, which the transforms implement."""
+    import random
+    import plonk_prototype_b200 as pb
+    rng = random.Random(7)
+    for log_n, world in ((14, 2), (16, 4), (22, 8), (26, 8)):
+        spec = pb.ShardSpec(log_n, world, 8)
+        log_m, log_g = log_n - 8, world.bit_length() - 1
+        log_cl, log_rl = log_m - log_g, 8 - log_g
+        for _ in range(200):
+            rank, e = rng.randrange(world), rng.randrange(spec.local)
+            j1, c = e >> log_cl, e & ((1 << log_cl) - 1)
+            j = (j1 << log_m) + (rank << log_cl) + c
+            assert spec.column_layout(j) == (rank, e)
+            r, kq = e >> log_m, e & ((1 << log_m) - 1)
+            i = ((rank << log_rl) + r) + (kq << 8)
+            assert spec.row_layout(i) == (rank, e)
