@@ -214,6 +214,11 @@ PB200_API int pb200_preprocess_sharded(pb200_ctx *ctx, const pb200_srs *srs_slic
  * With profiling on, pb200_profile_ms knows "prove.round1" … "prove.round5" (host wall-clock per round). */
 PB200_API int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk, const uint64_t *values_mont,
                           const uint32_t *pi_gate, const uint64_t *pi_mont, size_t n_pi, uint8_t proof_out[1040]);
+/* The same with the witness already in DEVICE memory (n_vars × 32 B, e.g. produced by a GPU witness generator or
+ * uploaded once with pb200_h2d): no bulk host→device copy inside the call.  Public inputs and the proof stay on the
+ * host (a few hundred bytes).  A gate index may appear at most once in pi_gate (both entry points; PB200_ERR_ARG). */
+PB200_API int pb200_prove_dev(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk, const uint64_t *values_mont_dev,
+                              const uint32_t *pi_gate, const uint64_t *pi_mont, size_t n_pi, uint8_t proof_out[1040]);
 /* ---- verifier (host CPU, as upstream's): dusk_plonk Proof::verify + OpeningKey::batch_check + the BLS12-381 pairing of
  * dusk_bls12_381.  No context and no GPU: the work is milliseconds and independent of n. ------- */
 /* vk_commitments: the 15 compressed commitments pb200_preprocess returns; n: padded circuit size; public inputs as for
@@ -245,6 +250,11 @@ PB200_API int pb200_synthetic_circuit(size_t n_gates, uint64_t seed, uint32_t n_
  * Profiling must have been switched on before that call. */
 PB200_API int pb200_profile_enable(pb200_ctx *ctx, int on);
 PB200_API int pb200_profile_ms(pb200_ctx *ctx, const char *name, float *ms);
+/* Every collected duration is also accumulated per name: pb200_profile_sum_ms returns the sum (and, optionally, the
+ * number of samples) since the last pb200_profile_reset — e.g. the total msm_accumulate_kernel time of one pb200_prove,
+ * which makes 11 MSM calls.  An unknown name reads as 0 ms / 0 samples. */
+PB200_API int pb200_profile_reset(pb200_ctx *ctx);
+PB200_API int pb200_profile_sum_ms(pb200_ctx *ctx, const char *name, float *ms, uint32_t *count);
 /* Number of kernels this library has launched on the context since init (bench.py's gpu_launches). */
 PB200_API uint64_t pb200_launch_count(const pb200_ctx *ctx);
 /* Integer-pipe microbenchmark: sustained IMAD.WIDE.U32.X (32×32+64 with carry) lane-operations per second

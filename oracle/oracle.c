@@ -341,13 +341,30 @@ ORC_API void orc_synthetic_bases(size_t n, uint64_t a, uint64_t d, uint64_t *out
     g1p_from_affine(&gp, &g);
     g1p_mul_u(&cur, &gp, &a, 1);
     g1p_mul_u(&step, &gp, &d, 1);
-    for (size_t i = 0; i < n; i++) {
-        g1a_t af;
-        g1a_from_proj(&af, &cur);
-        memcpy(out_xy + 12 * i, af.x.l, 48);
-        memcpy(out_xy + 12 * i + 6, af.y.l, 48);
-        g1p_add(&cur, &cur, &step);
+    /* normalise in chunks with one inversion each (Montgomery's trick): (a + i·d) ≢ 0 mod r for the sizes used, so Z ≠ 0 */
+    enum { CH = 1024 };
+    g1p_t *pts = malloc(CH * sizeof(g1p_t));
+    fp_t *pre = malloc(CH * sizeof(fp_t));
+    for (size_t base = 0; base < n; base += CH) {
+        const size_t m = n - base < CH ? n - base : CH;
+        for (size_t i = 0; i < m; i++) {
+            pts[i] = cur;
+            if (i == 0) pre[0] = cur.z; else fp_mul(&pre[i], &pre[i - 1], &cur.z);
+            g1p_add(&cur, &cur, &step);
+        }
+        fp_t inv;
+        fp_inv(&inv, &pre[m - 1]);
+        for (size_t i = m; i-- > 0;) {
+            fp_t zi, x, y;
+            if (i) { fp_mul(&zi, &inv, &pre[i - 1]); fp_mul(&inv, &inv, &pts[i].z); } else zi = inv;
+            fp_mul(&x, &pts[i].x, &zi);
+            fp_mul(&y, &pts[i].y, &zi);
+            memcpy(out_xy + 12 * (base + i), x.l, 48);
+            memcpy(out_xy + 12 * (base + i) + 6, y.l, 48);
+        }
     }
+    free(pts);
+    free(pre);
 }
 
 /* ------------------------------------------------------------------------------------ MSM */

@@ -180,9 +180,10 @@ def srs_setup(tau_mont, n):
     return out
 
 
-def plonk_prove(selectors, wires, values_mont, pi_pos, pi_mont, srs, label, threads=1):
+def plonk_prove(selectors, wires, values_mont, pi_pos, pi_mont, srs, label, threads=1, reps=None):
     """Preprocess + prove on the CPU.  selectors: 11 (n_gates, 4) uint64 arrays or None; wires: 4 uint32 arrays;
-    srs: (≥ n_pad, 12) packed affine points.  Returns (proof bytes, vk bytes, preprocess seconds, prove seconds)."""
+    srs: (≥ n_pad, 12) packed affine points.  Returns (proof bytes, vk bytes, preprocess seconds, prove seconds);
+    with reps = k the prove runs k times on the one preprocessed key and the last element is the list of k timings."""
     n_gates = len(wires[0])
     keep = []
     sel_arr = (ctypes.c_void_p * 11)()
@@ -209,12 +210,38 @@ def plonk_prove(selectors, wires, values_mont, pi_pos, pi_mont, srs, label, thre
     assert srs.shape[0] >= n_pad
     vk = ctypes.create_string_buffer(15 * 48)
     proof = ctypes.create_string_buffer(1040)
-    tm = (ctypes.c_double * 2)()
-    f = lib().orc_plonk_prove
+    k = 1 if reps is None else int(reps)
+    tm = (ctypes.c_double * (1 + k))()
+    f = lib().orc_plonk_prove_reps
     f.restype = ctypes.c_int
     rc = f(ctypes.c_size_t(n_gates), ctypes.c_size_t(vals.shape[0]), sel_arr, w_arr, ctypes.c_void_p(vals.ctypes.data),
            ctypes.c_void_p(pos.ctypes.data), ctypes.c_void_p(piv.ctypes.data), ctypes.c_size_t(pos.shape[0]),
-           ctypes.c_void_p(srs.ctypes.data), bytes(label), ctypes.c_size_t(len(label)), ctypes.c_int(threads), vk, proof, tm)
+           ctypes.c_void_p(srs.ctypes.data), bytes(label), ctypes.c_size_t(len(label)), ctypes.c_int(threads), vk, proof,
+           ctypes.c_int(k), tm)
     if rc != 0:
         raise RuntimeError("orc_plonk_prove failed: %d" % rc)
-    return proof.raw, vk.raw, tm[0], tm[1]
+    return proof.raw, vk.raw, tm[0], (tm[1] if reps is None else [tm[1 + i] for i in range(k)])
+
+
+def synthetic_circuit_columns(n_gates, seed=0x5EED, n_pub=2):
+    """The synthetic arithmetic circuit of bench.py assembled by the checker itself (orc_synthetic_circuit),
+    so the reference arm of bench.py never touches the product library.  Same return shape as
+    plonk_prototype_b200.synth.synthetic_circuit_columns: (selectors[11], wires[4], values_mont, pi_pos, pi_vals_mont)."""
+    assert n_gates >= 8 + n_pub and n_pub >= 1
+    steps = (n_gates - n_pub - 3) // 2
+    n_vars = 6 + 2 * steps + n_pub - 1
+    sel7 = [np.empty((n_gates, 4), np.uint64) for _ in range(7)]
+    wires = [np.empty(n_gates, np.uint32) for _ in range(4)]
+    values = np.empty((n_vars, 4), np.uint64)
+    pi_pos, pi_vals = np.empty(n_pub, np.uint32), np.empty((n_pub, 4), np.uint64)
+    sel_ptrs = (ctypes.c_void_p * 7)(*[a.ctypes.data for a in sel7])
+    wire_ptrs = (ctypes.c_void_p * 4)(*[a.ctypes.data for a in wires])
+    got = ctypes.c_size_t()
+    f = lib().orc_synthetic_circuit
+    f.restype = ctypes.c_int
+    rc = f(ctypes.c_size_t(n_gates), ctypes.c_uint64(seed), ctypes.c_uint32(n_pub), sel_ptrs, wire_ptrs, ctypes.c_void_p(values.ctypes.data),
+           ctypes.c_size_t(n_vars), ctypes.byref(got), ctypes.c_void_p(pi_pos.ctypes.data), ctypes.c_void_p(pi_vals.ctypes.data))
+    if rc != 0 or got.value != n_vars:
+        raise RuntimeError("orc_synthetic_circuit failed (%d)" % rc)
+    sel = [a if a.any() else None for a in sel7] + [None] * 4
+    return sel, wires, values, pi_pos, pi_vals

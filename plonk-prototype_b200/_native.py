@@ -20,10 +20,11 @@ EXPORTS = [
     "pb200_srs_upload", "pb200_srs_wrap_dev", "pb200_srs_precompute", "pb200_srs_free", "pb200_srs_len",
     "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_batch_dev", "pb200_g1_sum", "pb200_msm_window_bits",
     "pb200_srs_generate", "pb200_srs_generate_range", "pb200_srs_dev_ptr", "pb200_kzg_witness_dev", "pb200_fr_horner_step_dev",
-    "pb200_preprocess", "pb200_preprocess_sharded", "pb200_prover_key_free", "pb200_prover_key_size", "pb200_prover_key_bytes", "pb200_prove",
+    "pb200_preprocess", "pb200_preprocess_sharded", "pb200_prover_key_free", "pb200_prover_key_size", "pb200_prover_key_bytes", "pb200_prove", "pb200_prove_dev",
     "pb200_transcript_selftest", "pb200_synthetic_circuit", "pb200_verify", "pb200_opening_key_from_tau",
     "pb200_pairing_selftest",
-    "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_launch_count",
+    "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_profile_reset", "pb200_profile_sum_ms",
+    "pb200_launch_count",
     "pb200_imad_peak",
 ]
 
@@ -108,6 +109,7 @@ def lib():
         L.pb200_prover_key_bytes.argtypes = [vp]
         L.pb200_prover_key_bytes.restype = ctypes.c_size_t
         L.pb200_prove.argtypes = [vp, vp, vp, u64p, vp, u64p, ctypes.c_size_t, vp]
+        L.pb200_prove_dev.argtypes = [vp, vp, vp, u64p, vp, u64p, ctypes.c_size_t, vp]
         L.pb200_transcript_selftest.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p,
                                                 ctypes.c_char_p, ctypes.c_size_t]
         L.pb200_verify.argtypes = [vp, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, vp, vp, u64p, ctypes.c_size_t, u64p,
@@ -119,6 +121,8 @@ def lib():
         L.pb200_synthetic_bases_dev.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_uint64]
         L.pb200_profile_enable.argtypes = [vp, ctypes.c_int]
         L.pb200_profile_ms.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_float)]
+        L.pb200_profile_reset.argtypes = [vp]
+        L.pb200_profile_sum_ms.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint32)]
         L.pb200_launch_count.argtypes = [vp]
         L.pb200_launch_count.restype = ctypes.c_uint64
         L.pb200_imad_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
@@ -395,6 +399,16 @@ class Context:
                                       pos.shape[0], _ptr(out)))
         return out.tobytes()
 
+    def prove_dev(self, srs, pk, values_dev, pi_gate, pi_mont):
+        """`pb200_prove_dev`: the witness (n_vars × 32 B) is already in device memory."""
+        pos = np.ascontiguousarray(pi_gate, dtype=np.uint32)
+        piv = np.ascontiguousarray(pi_mont, dtype=np.uint64).reshape(-1, 4)
+        assert pos.shape[0] == piv.shape[0]
+        out = np.zeros(1040, np.uint8)
+        self._check(lib().pb200_prove_dev(self._h, srs, pk, ctypes.c_void_p(int(values_dev)), _ptr(pos) if pos.size else None,
+                                          _ptr(piv) if pos.size else None, pos.shape[0], _ptr(out)))
+        return out.tobytes()
+
     def synthetic_bases_dev(self, dev, n, a=0xB2000001, d=0x9E3779B1):
         self._check(lib().pb200_synthetic_bases_dev(self._h, ctypes.c_void_p(dev), n, a, d))
 
@@ -406,6 +420,15 @@ class Context:
         v = ctypes.c_float()
         self._check(lib().pb200_profile_ms(self._h, name.encode(), ctypes.byref(v)))
         return v.value
+
+    def profile_reset(self):
+        self._check(lib().pb200_profile_reset(self._h))
+
+    def profile_sum_ms(self, name):
+        """(Σ ms, samples) of timer `name` since the last profile_reset."""
+        v, c = ctypes.c_float(), ctypes.c_uint32()
+        self._check(lib().pb200_profile_sum_ms(self._h, name.encode(), ctypes.byref(v), ctypes.byref(c)))
+        return v.value, c.value
 
     def launch_count(self):
         return int(lib().pb200_launch_count(self._h))

@@ -104,6 +104,20 @@ extern "C" int pb200_profile_ms(pb200_ctx *ctx, const char *name, float *ms) {
     *ms = it->second;
     return 0;
 }
+extern "C" int pb200_profile_reset(pb200_ctx *ctx) {
+    if (!ctx) return PB200_ERR_ARG;
+    ctx->prof_sum.clear();
+    ctx->prof_cnt.clear();
+    return 0;
+}
+extern "C" int pb200_profile_sum_ms(pb200_ctx *ctx, const char *name, float *ms, uint32_t *count) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, name && ms);
+    auto it = ctx->prof_sum.find(name);
+    *ms = it != ctx->prof_sum.end() ? it->second : 0.0f;
+    if (count) *count = it != ctx->prof_sum.end() ? ctx->prof_cnt[name] : 0;
+    return 0;
+}
 extern "C" uint64_t pb200_launch_count(const pb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 // ---------------------------------------------------------------------------------------------------

@@ -19,7 +19,9 @@ struct pb200_ctx {
     std::string err;
     uint64_t launches = 0;
     bool profile = false;
-    std::map<std::string, float> prof_ms;
+    std::map<std::string, float> prof_ms;    // most recent duration per timer name
+    std::map<std::string, float> prof_sum;   // Σ of every collected duration since pb200_profile_reset
+    std::map<std::string, uint32_t> prof_cnt;
     // NTT state
     std::map<uint32_t, NttPlan *> ntt_plans;  // key: log_n | inverse << 8 | coset << 9
     void *ntt_scratch = nullptr;
@@ -91,7 +93,11 @@ struct PbTimer {
     void collect() {
         if (a && b) {
             float ms = 0;
-            if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) ctx->prof_ms[name] = ms;
+            if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) {
+                ctx->prof_ms[name] = ms;
+                ctx->prof_sum[name] += ms;
+                ctx->prof_cnt[name]++;
+            }
             cudaEventDestroy(a);
             cudaEventDestroy(b);
             a = b = nullptr;

@@ -339,8 +339,7 @@ static int ntt_build_plan(pb200_ctx *ctx, uint32_t L, int inverse, int coset, Nt
     pl->log_n = L;
     pl->inverse = inverse;
     pl->coset = coset;
-    *out = pl;  // owned by the ctx map from here on (freed in ntt_free_plans even on error)
-    ctx->ntt_plans[L | ((uint32_t)inverse << 8) | ((uint32_t)coset << 9)] = pl;
+    *out = pl;  // the caller caches it once it is complete (ntt_plan_discard on any failure)
     void *cbuf = nullptr;
     PB_CUDA(ctx, cudaMalloc(&cbuf, 4 * sizeof(Fr)));
     pl->allocs.push_back(cbuf);
@@ -451,6 +450,16 @@ static int ntt_build_plan(pb200_ctx *ctx, uint32_t L, int inverse, int coset, Nt
     return 0;
 }
 
+// A plan whose construction failed half-way (e.g. cudaMalloc of a 32·n-byte table) must not stay cached: the next
+// transform with the same key would launch on null tables.
+static void ntt_plan_discard(pb200_ctx *ctx, NttPlan *pl) {
+    if (!pl) return;
+    cudaStreamSynchronize(ctx->stream);  // fill kernels may still be writing the tables
+    for (void *a : pl->allocs) cudaFree(a);
+    delete pl;
+    (void)cudaGetLastError();
+}
+
 void ntt_free_plans(pb200_ctx *ctx) {
     for (auto &kv : ctx->ntt_plans) {
         for (void *a : kv.second->allocs) cudaFree(a);
@@ -466,8 +475,16 @@ static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset,
     if (L == 0) return 0;  // a one-point domain: every variant is the identity map
     NttPlan *pl = nullptr;
     auto it = ctx->ntt_plans.find(L | ((uint32_t)inverse << 8) | ((uint32_t)coset << 9));
-    if (it != ctx->ntt_plans.end()) pl = it->second;
-    else PB_TRY(ntt_build_plan(ctx, L, inverse, coset, &pl));
+    if (it != ctx->ntt_plans.end()) {
+        pl = it->second;
+    } else {
+        const int rc = ntt_build_plan(ctx, L, inverse, coset, &pl);
+        if (rc) {
+            ntt_plan_discard(ctx, pl);
+            return rc;
+        }
+        ctx->ntt_plans[L | ((uint32_t)inverse << 8) | ((uint32_t)coset << 9)] = pl;
+    }
     PbTimer timer(ctx, "ntt.total");
     if (pl->n_pass == 0) {
         for (uint32_t b = 0; b < batch; b++) {
@@ -549,6 +566,43 @@ extern "C" int pb200_ntt(pb200_ctx *ctx, uint64_t *data_host, uint32_t log_n, in
     return 0;
 }
 
+// Plan of the sharded four-step's column step (one pass, type 0): consts, two-level ω_n tables, ω_{n1} butterfly table.
+static int ntt_build_columns_plan(pb200_ctx *ctx, uint32_t log_n, uint32_t log_n1, int inverse, NttPlan **out) {
+    NttPlan *pl = new NttPlan();
+    pl->log_n = log_n;
+    pl->inverse = inverse;
+    *out = pl;
+    void *cbuf = nullptr;
+    PB_CUDA(ctx, cudaMalloc(&cbuf, 5 * sizeof(Fr)));
+    pl->allocs.push_back(cbuf);
+    pl->consts = (Fr *)cbuf;
+    ntt_consts_kernel<<<1, 1, 0, ctx->stream>>>(pl->consts, log_n, inverse);
+    PB_LAUNCHED(ctx);
+    const Fr *c_w = pl->consts + 0, *c_one = pl->consts + 3;
+    // n1⁻¹ = (2⁻¹)^log_n1: consts[1] holds 2^−log_n; reuse the constants kernel for a 2^log_n1 domain
+    Fr *c1 = nullptr;
+    void *c1buf = nullptr;
+    PB_CUDA(ctx, cudaMalloc(&c1buf, 4 * sizeof(Fr)));
+    pl->allocs.push_back(c1buf);
+    c1 = (Fr *)c1buf;
+    ntt_consts_kernel<<<1, 1, 0, ctx->stream>>>(c1, log_n1, inverse);
+    PB_LAUNCHED(ctx);
+    const uint32_t B = (log_n + 1) / 2;
+    Fr *lo = nullptr, *hi = nullptr, *tw = nullptr;
+    PB_TRY(fill_powers(ctx, pl, &lo, 1u << B, c_w, 1, c_one));
+    PB_TRY(fill_powers(ctx, pl, &hi, 1u << (log_n - B), c_w, 1ull << B, c_one));
+    PB_TRY(fill_powers(ctx, pl, &tw, 1u << (log_n1 - 1), c_w, 1ull << (log_n - log_n1), c_one));
+    NttPass &p = pl->pass[0];
+    memset(&p, 0, sizeof(p));
+    p.peer_log_rl = 0xffffffffu;
+    p.S = log_n1;
+    p.type = 0;
+    p.tw = tw;
+    if (!inverse) { p.store_mode = 2; p.s_lo = lo; p.s_hi = hi; p.s_B = B; }
+    else { p.load_mode = 3; p.l_lo = lo; p.l_hi = hi; p.l_B = B; p.store_mode = 1; p.s_const = c1 + 1; }
+    pl->n_pass = 1;
+    return 0;
+}
 // ---- sharded four-step building blocks (orchestrated by plonk-prototype_b200/dist_ntt.py) ----------
 // Column step of a 2^log_n transform split as n = n1·m over G ranks: this rank holds the n1 × cols matrix of its
 // column range [col_offset, col_offset + cols) (row-major, cols = 2^log_cols).
@@ -568,39 +622,12 @@ static int ntt_columns_impl(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, 
     if (it != ctx->ntt_plans.end()) {
         pl = it->second;
     } else {
-        pl = new NttPlan();
-        pl->log_n = log_n;
-        pl->inverse = inverse;
+        const int rc = ntt_build_columns_plan(ctx, log_n, log_n1, inverse, &pl);
+        if (rc) {
+            ntt_plan_discard(ctx, pl);
+            return rc;
+        }
         ctx->ntt_plans[key] = pl;
-        void *cbuf = nullptr;
-        PB_CUDA(ctx, cudaMalloc(&cbuf, 5 * sizeof(Fr)));
-        pl->allocs.push_back(cbuf);
-        pl->consts = (Fr *)cbuf;
-        ntt_consts_kernel<<<1, 1, 0, ctx->stream>>>(pl->consts, log_n, inverse);
-        PB_LAUNCHED(ctx);
-        const Fr *c_w = pl->consts + 0, *c_one = pl->consts + 3;
-        // n1⁻¹ = (2⁻¹)^log_n1: consts[1] holds 2^−log_n; reuse the constants kernel for a 2^log_n1 domain
-        Fr *c1 = nullptr;
-        void *c1buf = nullptr;
-        PB_CUDA(ctx, cudaMalloc(&c1buf, 4 * sizeof(Fr)));
-        pl->allocs.push_back(c1buf);
-        c1 = (Fr *)c1buf;
-        ntt_consts_kernel<<<1, 1, 0, ctx->stream>>>(c1, log_n1, inverse);
-        PB_LAUNCHED(ctx);
-        const uint32_t B = (log_n + 1) / 2;
-        Fr *lo = nullptr, *hi = nullptr, *tw = nullptr;
-        PB_TRY(fill_powers(ctx, pl, &lo, 1u << B, c_w, 1, c_one));
-        PB_TRY(fill_powers(ctx, pl, &hi, 1u << (log_n - B), c_w, 1ull << B, c_one));
-        PB_TRY(fill_powers(ctx, pl, &tw, 1u << (log_n1 - 1), c_w, 1ull << (log_n - log_n1), c_one));
-        NttPass &p = pl->pass[0];
-        memset(&p, 0, sizeof(p));
-        p.peer_log_rl = 0xffffffffu;
-        p.S = log_n1;
-        p.type = 0;
-        p.tw = tw;
-        if (!inverse) { p.store_mode = 2; p.s_lo = lo; p.s_hi = hi; p.s_B = B; }
-        else { p.load_mode = 3; p.l_lo = lo; p.l_hi = hi; p.l_B = B; p.store_mode = 1; p.s_const = c1 + 1; }
-        pl->n_pass = 1;
     }
     NttPass p = pl->pass[0];
     p.ncol_log = log_cols;

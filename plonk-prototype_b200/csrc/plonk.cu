@@ -508,7 +508,10 @@ struct RoundClock {
         if (!ctx->profile) return;
         cudaStreamSynchronize(ctx->stream);
         auto t1 = std::chrono::steady_clock::now();
-        ctx->prof_ms[name] = std::chrono::duration<float, std::milli>(t1 - t0).count();
+        const float ms = std::chrono::duration<float, std::milli>(t1 - t0).count();
+        ctx->prof_ms[name] = ms;
+        ctx->prof_sum[name] += ms;
+        ctx->prof_cnt[name]++;
         t0 = t1;
     }
 };
@@ -706,13 +709,28 @@ extern "C" int pb200_preprocess_sharded(pb200_ctx *ctx, const pb200_srs *srs, co
 #undef PK_LAUNCHED
 }
 
+static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk, const uint64_t *values_mont, bool values_on_device,
+                      const uint32_t *pi_gate, const uint64_t *pi_mont, size_t n_pi, uint8_t proof_out[1040]);
 extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk, const uint64_t *values_mont,
                            const uint32_t *pi_gate, const uint64_t *pi_mont, size_t n_pi, uint8_t proof_out[1040]) {
+    return prove_impl(ctx, srs, pk, values_mont, false, pi_gate, pi_mont, n_pi, proof_out);
+}
+extern "C" int pb200_prove_dev(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk, const uint64_t *values_mont_dev,
+                               const uint32_t *pi_gate, const uint64_t *pi_mont, size_t n_pi, uint8_t proof_out[1040]) {
+    return prove_impl(ctx, srs, pk, values_mont_dev, true, pi_gate, pi_mont, n_pi, proof_out);
+}
+static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk, const uint64_t *values_mont, bool values_on_device,
+                      const uint32_t *pi_gate, const uint64_t *pi_mont, size_t n_pi, uint8_t proof_out[1040]) {
     if (!ctx) return PB200_ERR_ARG;
     PB_ARG(ctx, srs != nullptr && pk != nullptr && values_mont != nullptr && proof_out != nullptr);
     PB_ARG(ctx, n_pi == 0 || (pi_gate != nullptr && pi_mont != nullptr));
     PB_ARG(ctx, pb200_srs_len(srs) >= pk->slice_n);
     for (size_t j = 0; j < n_pi; j++) PB_ARG(ctx, pi_gate[j] < pk->n);
+    if (n_pi > 1) {  // a gate carries one public input: duplicates would race in the scatter and disagree with the verifier's sum
+        std::vector<uint32_t> sorted(pi_gate, pi_gate + n_pi);
+        std::sort(sorted.begin(), sorted.end());
+        PB_ARG(ctx, std::adjacent_find(sorted.begin(), sorted.end()) == sorted.end());
+    }
     PB_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const size_t n = pk->n, N4 = 4 * n;
@@ -729,8 +747,12 @@ extern "C" int pb200_prove(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_ke
     Fr *tilesA = pk->small + 64, *tilesB = tilesA + scan_tiles(n), *partial = tilesB + scan_tiles(n);
 
     // ---- round 1: wire polynomials --------------------------------------------------------------------------------
-    PB_CUDA(ctx, cudaMemcpyAsync(pk->values, values_mont, pk->n_vars * sizeof(Fr), cudaMemcpyHostToDevice, st));
-    gather_wires_kernel<<<dim3(cdiv(n, 256), 4), 256, 0, st>>>(pk->w_evals, pk->wires, pk->values, (uint32_t)pk->n_gates, n32);
+    const Fr *values_dev = (const Fr *)values_mont;
+    if (!values_on_device) {
+        PB_CUDA(ctx, cudaMemcpyAsync(pk->values, values_mont, pk->n_vars * sizeof(Fr), cudaMemcpyHostToDevice, st));
+        values_dev = pk->values;
+    }
+    gather_wires_kernel<<<dim3(cdiv(n, 256), 4), 256, 0, st>>>(pk->w_evals, pk->wires, values_dev, (uint32_t)pk->n_gates, n32);
     PB_LAUNCHED(ctx);
     PB_CUDA(ctx, cudaMemcpyAsync(pk->w_poly, pk->w_evals, 4 * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     PB_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)pk->w_poly, log_n, 4, 1, 0));

@@ -12,6 +12,7 @@
 // over |x| = 0xd201000000010000; the sign of x only conjugates the result, which does not change whether a product of
 // pairings is one.  Final exponentiation: (p⁶ − 1) by conjugation and inversion, then (p⁶ + 1)/r by plain
 // square-and-multiply (≈ 2000 squarings — milliseconds; no Frobenius tables to get wrong).
+#include <algorithm>
 #include <cstring>
 #include <utility>
 #include <vector>
@@ -335,6 +336,11 @@ extern "C" int pb200_verify(const uint8_t vk_commitments[15 * 48], size_t n, con
         return PB200_ERR_ARG;
     if (n < 2 || (n & (n - 1)) || n > ((size_t)1 << 30)) return PB200_ERR_ARG;
     *accepted = 0;
+    if (n_pi > 1) {  // one public input per gate, as pb200_prove requires (a duplicate would be summed here but overwritten there)
+        std::vector<uint32_t> sorted(pi_gate, pi_gate + n_pi);
+        std::sort(sorted.begin(), sorted.end());
+        if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) return PB200_ERR_ARG;
+    }
     enum { Q_M, Q_L, Q_R, Q_O, Q_C, Q_4, Q_ARITH, Q_RANGE, Q_LOGIC, Q_FIXED, Q_VAR, S1, S2, S3, S4 };
     G1A vk[15], pr[11];
     for (int i = 0; i < 15; i++)

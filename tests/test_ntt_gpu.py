@@ -59,6 +59,29 @@ def test_matches_oracle_large(ctx, oracle, log_n):
         assert (got == want).all(), (log_n, name)
 
 
+@pytest.mark.parametrize("log_n,variants", [(24, (0, 1, 2, 3)), (26, (0,))])
+def test_full_vector_matches_oracle_at_baseline_sizes(ctx, oracle, log_n, variants):
+    """BASELINE.json configs[2] at its largest sizes, every output element against the CPU restatement (all host threads):
+    2^24 in all four variants, 2^26 forward."""
+    import os
+    n = 1 << log_n
+    x = oracle.random_fr(0xF1F00000 + log_n, n)           # raw limbs < r are valid Montgomery representations
+    threads = os.cpu_count() or 8
+    d = ctx.malloc(x.nbytes)
+    try:
+        got = np.empty_like(x)
+        for v in variants:
+            name, inv, cos = VARIANTS[v]
+            ctx.h2d(d, x)
+            ctx.ntt_dev(d, log_n, inv, cos)
+            ctx.d2h(got, d)
+            want = oracle.ntt(x, inv, cos, threads=threads)
+            assert (got == want).all(), (log_n, name, int((got != want).any(axis=1).sum()))
+            del want
+    finally:
+        ctx.free(d)
+
+
 def test_edge_vectors(ctx, oracle):
     for log_n in (5, 12, 14):
         n = 1 << log_n

@@ -341,3 +341,75 @@ def test_fr_horner_step(ctx):
     assert (got == mont(want)).all()
     ctx.free(a_dev)
     ctx.free(p_dev)
+
+
+def test_prove_dev_equals_prove_and_profile_sums(ctx):
+    """pb200_prove_dev (witness already in HBM) returns the bytes pb200_prove returns; the accumulated profile sums count
+    every MSM call of the proof (4 batched launches = 11 commitments)."""
+    import plonk_prototype_b200 as pb
+    from plonk_prototype_b200.synth import synthetic_circuit_columns
+    n = 1 << 12
+    sel, wires, values, pi_pos, pi_vals = synthetic_circuit_columns(n)
+    pp = pb.PublicParameters(n - 1, 0xD3F, ctx)
+    pk, _ = ctx.preprocess(pp.srs, sel, wires, values.shape[0], b"dev")
+    want = ctx.prove(pp.srs, pk, values, pi_pos, pi_vals)
+    d = ctx.malloc(values.nbytes)
+    try:
+        ctx.h2d(d, values)
+        ctx.profile_enable(True)
+        ctx.profile_reset()
+        got = ctx.prove_dev(pp.srs, pk, d, pi_pos, pi_vals)
+        ms, count = ctx.profile_sum_ms("msm.accumulate")
+        ctx.profile_enable(False)
+        assert got == want
+        assert count == 4 and ms > 0.0
+        assert ctx.profile_sum_ms("no.such.timer") == (0.0, 0)
+        ctx.profile_reset()
+        assert ctx.profile_sum_ms("msm.accumulate") == (0.0, 0)
+    finally:
+        ctx.free(d)
+        ctx.prover_key_free(pk)
+        pp.close()
+
+
+def test_duplicate_public_input_positions_are_rejected(ctx):
+    """A gate carries one public input: prover (scatter would race) and verifier (would sum) both refuse duplicates."""
+    import plonk_prototype_b200 as pb
+    from plonk_prototype_b200.synth import synthetic_circuit_columns
+    n = 64
+    sel, wires, values, pi_pos, pi_vals = synthetic_circuit_columns(n)
+    pp = pb.PublicParameters(n - 1, 0x77, ctx)
+    pk, vk = ctx.preprocess(pp.srs, sel, wires, values.shape[0], b"dup")
+    try:
+        proof = ctx.prove(pp.srs, pk, values, pi_pos, pi_vals)
+        dup_pos = np.array([pi_pos[0], pi_pos[0]], dtype=np.uint32)
+        with pytest.raises(pb.Pb200Error):
+            ctx.prove(pp.srs, pk, values, dup_pos, pi_vals)
+        bh = pb.opening_key_from_tau(pb.scalars_to_mont([0x77]))
+        assert pb.verify(vk, n, b"dup", proof, pi_pos, pi_vals, bh)
+        with pytest.raises(pb.Pb200Error):
+            pb.verify(vk, n, b"dup", proof, dup_pos, pi_vals, bh)
+    finally:
+        ctx.prover_key_free(pk)
+        pp.close()
+
+
+def test_proof_2_20_gates_byte_identical_with_c_restatement(ctx, oracle):
+    """BASELINE.json configs[3] at full size, whole proof: the C restatement proves the same 2^20-gate circuit on the
+    GPU's own commit key (copied back to the host) with every host thread; the 1040 bytes and the verifier key match."""
+    import os
+    import plonk_prototype_b200 as pb
+    from plonk_prototype_b200.synth import synthetic_circuit_columns
+    L, tau, label = 20, 0xB2000014, b"pb200-full-bytes"
+    n = 1 << L
+    sel, wires, values, pi_pos, pi_vals = synthetic_circuit_columns(n)
+    pp = pb.PublicParameters(n - 1, tau, ctx)
+    pk, vkb = ctx.preprocess(pp.srs, sel, wires, values.shape[0], label)
+    proof = ctx.prove(pp.srs, pk, values, pi_pos, pi_vals)
+    srs_host = np.zeros((n, 12), np.uint64)
+    ctx.d2h(srs_host, ctx.srs_dev_ptr(pp.srs))
+    ctx.prover_key_free(pk)
+    pp.close()
+    want_proof, want_vk, _, _ = oracle.plonk_prove(sel, wires, values, pi_pos, pi_vals, srs_host, label, threads=os.cpu_count() or 8)
+    assert vkb == want_vk
+    assert proof == want_proof
