@@ -11,6 +11,8 @@
 // bit-reversal, the inter-pass twiddle ω_n^{j·k}, the coset powers 7^{±j} and the n⁻¹ scaling fused
 // into the load / store.  Tiles are contiguous along the column axis, so global accesses are
 // C·32-byte runs (one 32-byte sector per element at worst).
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstring>
 #include "common.cuh"
@@ -95,6 +97,8 @@ __device__ __forceinline__ void bfly1(Fr &a, Fr &b) {  // w = 1
     b = a - b;
     a = s;
 }
+
+#include "ntt_tma.cuh"
 
 // Three DIF stages on bits [b_lo, b_lo+2] (b_lo ≥ 1) of the eight points a thread holds; v = x mod 2^b_lo.
 __device__ __forceinline__ void radix8_general(Fr (&a)[8], const Fr *tw, uint32_t v, uint32_t b_lo, uint32_t S) {
@@ -314,6 +318,8 @@ struct NttPlan {
     int inverse = 0, coset = 0;
     int n_pass = 0;
     NttPass pass[3];
+    bool tma = false;        // every pass also has a TMA description (ntt_pass_tma_kernel); same tables, same tile shape
+    NttPassTma tpass[3];
     Fr *consts = nullptr;
     std::vector<void *> allocs;
     size_t table_bytes = 0;
@@ -349,7 +355,12 @@ static int ntt_build_plan(pb200_ctx *ctx, uint32_t L, int inverse, int coset, Nt
     const Fr *c_w = pl->consts + 0, *c_ninv = pl->consts + 1, *c_g = pl->consts + 2, *c_one = pl->consts + 3;
     if (L < 3) { pl->n_pass = 0; return 0; }
 
-    const int P = L <= kTileLogMax ? 1 : (L <= 2 * kTileLogMax ? 2 : 3);
+    // Plan shape.  "tma": tiles of 2^S points × 4 columns with S ≤ 9 (two passes up to 2^18, three up to 2^27), the shape
+    // ntt_pass_tma_kernel is built for — 128-byte runs in global memory for every pass.  Otherwise (tiny and huge domains,
+    // PB200_NTT_PLAN=legacy): as few passes as an 2^11-point tile allows, columns per tile from the tile size.
+    const char *plan_env = getenv("PB200_NTT_PLAN");
+    const bool tma_shape = !(plan_env && !strcmp(plan_env, "legacy")) && L >= env_u32("PB200_NTT_TMA_MIN_LOG", 12) && L <= 27;
+    const int P = tma_shape ? (L <= 18 ? 2 : 3) : (L <= kTileLogMax ? 1 : (L <= 2 * kTileLogMax ? 2 : 3));
     uint32_t S[3] = {0, 0, 0};
     if (P == 1) S[0] = L;
     else if (P == 2) { S[0] = (L + 1) / 2; S[1] = L - S[0]; }
@@ -400,7 +411,7 @@ static int ntt_build_plan(pb200_ctx *ctx, uint32_t L, int inverse, int coset, Nt
         if (!last) {
             p.type = 0;
             p.ncol_log = L - done - S[i];
-            p.logC = std::min(tile_log_for(S[i]) - S[i], p.ncol_log);
+            p.logC = tma_shape ? 2 : std::min(tile_log_for(S[i]) - S[i], p.ncol_log);
             p.store_mode = 2;
             p.mult_log = done;  // ω_m^{j·k} with m = n / 2^done equals ω_n^{(j·k) << done}
             p.s_lo = lo;
@@ -420,7 +431,7 @@ static int ntt_build_plan(pb200_ctx *ctx, uint32_t L, int inverse, int coset, Nt
             p.type = 1;
             p.nrows_log = L - S[i];
             p.n1_log = (P == 3) ? S[0] : p.nrows_log;
-            p.logC = std::min(tile_log_for(S[i]) - S[i], p.nrows_log);
+            p.logC = tma_shape ? 2 : std::min(tile_log_for(S[i]) - S[i], p.nrows_log);
             if (inverse && coset) {
                 p.store_mode = 3; p.s_lo = clo; p.s_hi = chi; p.s_B = B;
                 if (full_ok(L)) {
@@ -447,6 +458,31 @@ static int ntt_build_plan(pb200_ctx *ctx, uint32_t L, int inverse, int coset, Nt
         }
         done += S[i];
     }
+    // TMA description of the same passes: needs the single-lookup tables (one multiply per element) throughout
+    if (tma_shape && pb_encode_tiled() != nullptr) {
+        bool ok = true;
+        for (int i = 0; i < P && ok; i++) {
+            const NttPass &p = pl->pass[i];
+            ok = p.S >= 6 && p.S <= 9 && p.logC == 2 && (p.load_mode == 0 || p.load_mode == 2) &&
+                 (p.type == 0 ? p.store_mode == 4 : (p.store_mode == 0 || p.store_mode == 5));
+        }
+        for (int i = 0; i < P && ok; i++) {
+            const NttPass &p = pl->pass[i];
+            NttPassTma &t = pl->tpass[i];
+            memset(&t, 0, sizeof(t));
+            t.S = p.S; t.type = p.type; t.ncol_log = p.ncol_log; t.nrows_log = p.nrows_log; t.n1_log = p.n1_log;
+            t.load_mode = p.load_mode; t.store_mode = p.store_mode; t.l_full = p.l_full; t.s_full = p.s_full;
+            const uint32_t entries = ntt_tw_image_entries(p.S);
+            void *img = nullptr;
+            PB_CUDA(ctx, cudaMalloc(&img, (size_t)entries * sizeof(Fr)));
+            pl->allocs.push_back(img);
+            ntt_tw_image_kernel<<<(entries + 127) / 128, 128, 0, ctx->stream>>>((Fr *)img, p.tw, p.S);
+            PB_LAUNCHED(ctx);
+            t.tw_img = (const Fr *)img;
+            t.tw_bytes = entries * (uint32_t)sizeof(Fr);
+        }
+        pl->tma = ok;
+    }
     return 0;
 }
 
@@ -469,6 +505,40 @@ void ntt_free_plans(pb200_ctx *ctx) {
     if (ctx->ntt_scratch) cudaFree(ctx->ntt_scratch);
     ctx->ntt_scratch = nullptr;
     ctx->ntt_scratch_bytes = 0;
+}
+
+// ntt_pass_tma_kernel instantiations: S ∈ 6…9 × resident-thread budget (512 threads/SM = 128 registers, 384 = 168).
+typedef void (*NttTmaKernel)(const CUtensorMap, const CUtensorMap, const Fr *, const NttPassTma);
+static NttTmaKernel ntt_tma_kernel_for(uint32_t S, bool wide_regs) {
+    switch (S) {
+        case 6: return wide_regs ? ntt_pass_tma_kernel<6, 384> : ntt_pass_tma_kernel<6, 512>;
+        case 7: return wide_regs ? ntt_pass_tma_kernel<7, 384> : ntt_pass_tma_kernel<7, 512>;
+        case 8: return wide_regs ? ntt_pass_tma_kernel<8, 384> : ntt_pass_tma_kernel<8, 512>;
+        case 9: return wide_regs ? ntt_pass_tma_kernel<9, 384> : ntt_pass_tma_kernel<9, 512>;
+    }
+    return nullptr;
+}
+static size_t ntt_tma_smem_bytes(uint32_t S) {
+    return 1024 + ((size_t)32 << (S + 2)) + (((size_t)ntt_tw_image_entries(S) * sizeof(Fr) + 15) & ~(size_t)15) + 16;
+}
+// One pass over `nb` vectors of 2^L scalars (src / dst point at the first of them).
+static int ntt_launch_tma(pb200_ctx *ctx, const NttPassTma &tp, const Fr *src, Fr *dst, uint32_t L, uint32_t blocks, uint32_t nb) {
+    static const bool wide_regs = getenv("PB200_NTT_TMA_REGS") && !strcmp(getenv("PB200_NTT_TMA_REGS"), "168");
+    const uint32_t box_rows = std::min(1u << tp.S, 256u);
+    CUtensorMap map_in, map_out;
+    if (tp.type == 0) {
+        const uint64_t cols = 1ull << tp.ncol_log, rows = (uint64_t)nb << (L - tp.ncol_log);
+        PB_TRY(pb_make_tile_map(ctx, &map_in, src, cols, rows, box_rows));
+        PB_TRY(pb_make_tile_map(ctx, &map_out, dst, cols, rows, box_rows));
+    } else {
+        PB_TRY(pb_make_tile_map(ctx, &map_out, dst, 1ull << tp.nrows_log, (uint64_t)nb << tp.S, box_rows));
+        map_in = map_out;   // rows are staged through registers: no input map
+    }
+    NttTmaKernel k = ntt_tma_kernel_for(tp.S, wide_regs);
+    PB_ARG(ctx, k != nullptr);
+    k<<<dim3(blocks, nb), 1u << (tp.S - 1), ntt_tma_smem_bytes(tp.S), ctx->stream>>>(map_in, map_out, src, tp);
+    PB_LAUNCHED(ctx);
+    return 0;
 }
 
 static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset, uint32_t batch = 1) {
@@ -509,8 +579,15 @@ static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset,
             Fr *dst = (i == pl->n_pass - 1) ? data : scratch;
             NttPass pb = p;
             pb.batch_log = L;
+            static const bool force_legacy = getenv("PB200_NTT_KERNEL") && !strcmp(getenv("PB200_NTT_KERNEL"), "legacy");
             for (uint32_t b0 = 0; b0 < batch; b0 += 32768) {  // gridDim.y ≤ 65535
                 const uint32_t nb = std::min<uint32_t>(32768, batch - b0);
+                if (pl->tma && !force_legacy) {
+                    NttPassTma tp = pl->tpass[i];
+                    tp.batch_log = L;
+                    PB_TRY(ntt_launch_tma(ctx, tp, src + ((size_t)b0 << L), dst + ((size_t)b0 << L), L, blocks, nb));
+                    continue;
+                }
                 ntt_pass_kernel<<<dim3(blocks, nb), threads, smem, ctx->stream>>>(src + ((size_t)b0 << L), dst + ((size_t)b0 << L), pb);
                 PB_LAUNCHED(ctx);
             }
@@ -527,6 +604,10 @@ static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset,
 int ntt_module_init(pb200_ctx *ctx) {
     PB_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       8 * (1 << kTileLogMax) * 4));
+    for (uint32_t S = 6; S <= 9; S++)
+        for (int w = 0; w < 2; w++)
+            PB_CUDA(ctx, cudaFuncSetAttribute(ntt_tma_kernel_for(S, w != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)ntt_tma_smem_bytes(S)));
     return 0;
 }
 
