@@ -169,8 +169,8 @@ typedef struct pb200_circuit {
  * polynomials (15 iNTT + 15 MSM), extends them to the 4n coset (15 coset NTTs), and seeds Transcript::new(label) with
  * the verifier key.  Everything stays resident in HBM behind the returned handle.  vk_commitments (optional) receives
  * the 15 compressed commitments in the column order above followed by left/right/out/fourth sigma.
- * Only the arithmetic and range widgets are implemented: non-zero q_logic / q_fixed_group_add / q_variable_group_add
- * columns are rejected (PB200_ERR_ARG). */
+ * Widgets: arithmetic, range, logic, fixed-base scalar multiplication and variable-base point addition on JubJub (all
+ * eleven selector columns of StandardComposer). */
 PB200_API int pb200_preprocess(pb200_ctx *ctx, const pb200_srs *srs, const pb200_circuit *circuit, const uint8_t *transcript_label,
                                size_t label_len, pb200_prover_key **out, uint8_t vk_commitments[15 * 48]);
 PB200_API void pb200_prover_key_free(pb200_ctx *ctx, pb200_prover_key *pk);

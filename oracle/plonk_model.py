@@ -177,10 +177,11 @@ class Composer:
         self.values.append(v % R)
         return len(self.values) - 1
 
-    def poly_gate(self, a, b, c, d, q_m=0, q_l=0, q_r=0, q_o=0, q_c=0, q_4=0, pi=0, q_arith=1, q_range=0):
+    def poly_gate(self, a, b, c, d, q_m=0, q_l=0, q_r=0, q_o=0, q_c=0, q_4=0, pi=0, q_arith=1, q_range=0, q_logic=0, q_fixed=0,
+                  q_var=0):
         for k, v in (("q_m", q_m), ("q_l", q_l), ("q_r", q_r), ("q_o", q_o), ("q_c", q_c), ("q_4", q_4),
-                     ("q_arith", q_arith), ("q_range", q_range), ("q_logic", 0), ("q_fixed_group_add", 0),
-                     ("q_variable_group_add", 0)):
+                     ("q_arith", q_arith), ("q_range", q_range), ("q_logic", q_logic), ("q_fixed_group_add", q_fixed),
+                     ("q_variable_group_add", q_var)):
             self.q[k].append(v % R)
         for col, var in zip(self.w, (a, b, c, d)):
             col.append(var)
@@ -213,6 +214,90 @@ class Composer:
         self.constrain_to_constant(var, v, 0)
         return var
 
+    def assert_equal(self, a, b):
+        self.poly_gate(a, b, self.zero_var, self.zero_var, q_l=1, q_r=-1)
+
+    # ---- ECC gadgets on JubJub (dusk-plonk constraint_system::ecc; call sites /root/reference/src/zk/gadgets.rs:34,37,40,
+    # circuits.rs:64-65).  A Point is a pair of variables (x, y).
+    def fixed_base_scalar_mul(self, scalar_var, generator):
+        """256 rows of the fixed-base widget (2-bit windowed NAF ladder from the most significant digit) plus one plain row
+        carrying the final accumulators; the scalar accumulator is constrained to equal `scalar_var`."""
+        num_bits = 256
+        multiples = [generator]
+        for _ in range(num_bits - 1):
+            multiples.append(jj_add(multiples[-1], multiples[-1]))
+        multiples.reverse()                                           # multiples[i] pairs with the i-th digit from the top
+        k = self.values[scalar_var]
+        assert k < JJ_ORDER, "JubJubScalar::from_bytes(..).unwrap(): the scalar must be below the JubJub group order"
+        naf = wnaf2(k)                                               # 256 digits in {−1, 0, 1}, least significant first
+        scalar_acc, point_acc, xy_alphas = [0], [(0, 1)], []
+        for i, entry in enumerate(reversed(naf)):
+            bx, by = multiples[i]
+            to_add = (0, 1) if entry == 0 else ((bx, by) if entry == 1 else ((-bx) % R, by))
+            scalar_acc.append((2 * scalar_acc[i] + entry) % R)
+            point_acc.append(jj_add(point_acc[i], to_add))
+            xy_alphas.append(to_add[0] * to_add[1] % R)
+        for i in range(num_bits):
+            acc_x, acc_y = self.add_input(point_acc[i][0]), self.add_input(point_acc[i][1])
+            acc_bit = self.add_input(scalar_acc[i])
+            if i == 0:
+                self.constrain_to_constant(acc_x, 0, 0)
+                self.constrain_to_constant(acc_y, 1, 0)
+                self.constrain_to_constant(acc_bit, 0, 0)
+            bx, by = multiples[i]
+            xy_alpha = self.add_input(xy_alphas[i])
+            self.poly_gate(acc_x, acc_y, xy_alpha, acc_bit, q_l=bx, q_r=by, q_c=bx * by, q_arith=0, q_fixed=1)
+        acc_x, acc_y = self.add_input(point_acc[num_bits][0]), self.add_input(point_acc[num_bits][1])
+        last_bit = self.add_input(scalar_acc[num_bits])
+        self.poly_gate(acc_x, acc_y, self.zero_var, last_bit)        # big_add_gate with zero selectors: the "next" row of gate 255
+        self.assert_equal(last_bit, scalar_var)
+        return (acc_x, acc_y)
+
+    def point_addition_gate(self, p1, p2):
+        (x1, y1), (x2, y2) = p1, p2
+        v = self.values
+        x3v, y3v = jj_add((v[x1], v[y1]), (v[x2], v[y2]))
+        x1y2 = self.add_input(v[x1] * v[y2])
+        x3, y3 = self.add_input(x3v), self.add_input(y3v)
+        self.poly_gate(x1, y1, x2, y2, q_arith=0, q_var=1)
+        self.poly_gate(x3, y3, self.zero_var, x1y2, q_arith=0)
+        return (x3, y3)
+
+    def assert_equal_public_point(self, point, affine):
+        self.constrain_to_constant(point[0], 0, -affine[0])
+        self.constrain_to_constant(point[1], 0, -affine[1])
+
+    # ---- logic widget: XOR / AND of two num_bits-bit values, one 2-bit quad per row from the top (constraint_system::logic)
+    def logic_gate(self, a, b, num_bits, is_xor):
+        assert num_bits % 2 == 0
+        av, bv = self.values[a], self.values[b]
+        nq = num_bits // 2
+        sel = -1 if is_xor else 1
+        rows_l, rows_r, rows_4, rows_o = [self.zero_var], [self.zero_var], [self.zero_var], []
+        la = ra = oa = 0
+        for i in range(nq):
+            sh = 2 * (nq - 1 - i)
+            lq, rq = (av >> sh) & 3, (bv >> sh) & 3
+            oq = (lq ^ rq) if is_xor else (lq & rq)
+            la, ra, oa = 4 * la + lq, 4 * ra + rq, 4 * oa + oq
+            rows_l.append(self.add_input(la))
+            rows_r.append(self.add_input(ra))
+            rows_4.append(self.add_input(oa))
+            rows_o.append(self.add_input(lq * rq))
+        rows_o.append(self.zero_var)
+        for i in range(nq + 1):
+            last = i == nq
+            self.poly_gate(rows_l[i], rows_r[i], rows_o[i], rows_4[i], q_arith=0, q_c=0 if last else sel, q_logic=0 if last else sel)
+        self.assert_equal(a, rows_l[nq])
+        self.assert_equal(b, rows_r[nq])
+        return rows_4[nq]
+
+    def xor_gate(self, a, b, num_bits):
+        return self.logic_gate(a, b, num_bits, True)
+
+    def and_gate(self, a, b, num_bits):
+        return self.logic_gate(a, b, num_bits, False)
+
     def add_dummy_constraints(self):
         six, one, seven, m20 = (self.add_input(v) for v in (6, 1, 7, -20))
         self.poly_gate(six, seven, m20, one, q_m=1, q_l=2, q_r=3, q_o=4, q_c=4, q_4=1)
@@ -227,6 +312,18 @@ class Composer:
             t = q["q_arith"] * (q["q_m"] * a * b + q["q_l"] * a + q["q_r"] * b + q["q_o"] * c + q["q_4"] * d + q["q_c"])
             if (t + self.pi.get(i, 0)) % R:
                 return False
+            j = (i + 1) % self.n
+            an, bn, dn = v[self.w[0][j]], v[self.w[1][j]], v[self.w[3][j]]
+            # every separation challenge must make the widget vanish: test with two unrelated values
+            for sep in (3, 0x1234567):
+                if q["q_range"] and _range_term(a, b, c, d, dn, sep):
+                    return False
+                if q["q_logic"] and _logic_term(a, an, b, bn, c, d, dn, q["q_c"], sep):
+                    return False
+                if q["q_fixed_group_add"] and _fixed_base_term(a, an, b, bn, c, d, dn, q["q_l"], q["q_r"], q["q_c"], sep):
+                    return False
+                if q["q_variable_group_add"] and _var_base_term(a, an, b, bn, c, d, dn, sep):
+                    return False
         return True
 
 
@@ -343,6 +440,85 @@ def _range_term(a, b, c, d, d_next, sep):
             + kappa * kappa * kappa * _delta(d_next - 4 * a)) * sep % R
 
 
+# JubJub (dusk-jubjub 0.10, /root/reference/Cargo.toml:21): −x² + y² = 1 + d·x²·y² over Fr, d = −10240/10241.  The two
+# generators the reference's gadgets use (gadgets.rs:34,37): GENERATOR has y = 18 (the x below is the root of the curve
+# equation with that y, prime-order subgroup); GENERATOR_NUMS as published.  Both are checked on-curve and of order
+# JJ_ORDER in tests/test_prover_cpu.py — the constants are pinned by the curve, not by memory.
+EDWARDS_D = (-10240 * pow(10241, -1, R)) % R
+JJ_ORDER = 0x0E7DB4EA6533AFA906673B0101343B00A6682093CCC81082D0970E5ED6F72CB7
+JJ_GENERATOR = (0x3FD2814C43AC65A6F1FBF02D0FD6CCE62E3EBB21FD6C54ED4DF7B7FFEC7BEACA, 0x12)
+JJ_GENERATOR_NUMS = (0x5E67B8F316F414F7BD9514C773FD4456931E316A39FE4541921710179DF76377,
+                     0x43D80EB3B2F3EB1B7B162DBEEB3B34FD9949BA0F82A5507A6705B707162E3EF8)
+
+
+def jj_add(p, q):
+    (x1, y1), (x2, y2) = p, q
+    t = EDWARDS_D * x1 % R * x2 % R * y1 % R * y2 % R
+    return ((x1 * y2 + y1 * x2) * pow(1 + t, -1, R) % R, (y1 * y2 + x1 * x2) * pow(1 - t, -1, R) % R)
+
+
+def jj_mul(p, k):
+    acc = (0, 1)
+    while k:
+        if k & 1:
+            acc = jj_add(acc, p)
+        p = jj_add(p, p)
+        k >>= 1
+    return acc
+
+
+def wnaf2(k):
+    """Fr::compute_windowed_naf(2): 256 digits in {−1, 0, 1}, least significant first (non-adjacent form)."""
+    out = [0] * 256
+    i = 0
+    while k >= 1:
+        if k & 1:
+            d = 2 - (k & 3)            # k mod 4 = 1 → 1, = 3 → −1
+            out[i] = d
+            k -= d
+        k >>= 1
+        i += 1
+    return out
+
+
+def _logic_term(a, a_next, b, b_next, c, d, d_next, q_c, sep):
+    """logic widget: quads a' = a_next − 4a, b' = b_next − 4b, out d' = d_next − 4d, product w = c."""
+    kappa = sep * sep % R
+    k2, k3, k4 = kappa * kappa % R, pow(kappa, 3, R), pow(kappa, 4, R)
+    qa, qb, qd, w = (a_next - 4 * a) % R, (b_next - 4 * b) % R, (d_next - 4 * d) % R, c
+    f = w * (w * (4 * w - 18 * (qa + qb) + 81) + 18 * (qa * qa + qb * qb) - 81 * (qa + qb) + 83)
+    e = 3 * (qa + qb + qd) - 2 * f
+    bb = q_c * (9 * qd - 3 * (qa + qb))
+    return (_delta(qa) + _delta(qb) * kappa + _delta(qd) * k2 + (w - qa * qb) * k3 + (bb + e) * k4) % R * sep % R
+
+
+def _fixed_base_term(a, a_next, b, b_next, c, d, d_next, q_l, q_r, q_c, sep):
+    """fixed-base widget: acc (a, b) + bit·(x_β, y_β) = (a_next, b_next) on JubJub, bit = d_next − 2d ∈ {−1, 0, 1}, c = x_α·y_α."""
+    kappa = sep * sep % R
+    k2, k3 = kappa * kappa % R, pow(kappa, 3, R)
+    bit = (d_next - 2 * d) % R
+    bit_cons = bit * (bit - 1) * (bit + 1)
+    y_alpha = bit * bit * (q_r - 1) + 1
+    x_alpha = bit * q_l
+    xy_cons = (bit * q_c - c) * kappa
+    t = c * a % R * b % R * EDWARDS_D % R
+    x_cons = (a_next + a_next * t - (a * y_alpha + b * x_alpha)) * k2
+    y_cons = (b_next - b_next * t - (b * y_alpha + a * x_alpha)) * k3
+    return (bit_cons + x_cons + y_cons + xy_cons) % R * sep % R
+
+
+def _var_base_term(a, a_next, b, b_next, c, d, d_next, sep):
+    """variable-base widget: (x1, y1) = (a, b), (x2, y2) = (c, d), (x3, y3) = (a_next, b_next), x1·y2 = d_next."""
+    kappa = sep * sep % R
+    x1, y1, x2, y2, x3, y3, x1y2 = a, b, c, d, a_next, b_next, d_next
+    y1x2, y1y2, x1x2 = y1 * x2 % R, y1 * y2 % R, x1 * x2 % R
+    xy_cons = x1 * y2 - x1y2
+    t = EDWARDS_D * x1y2 % R * y1x2 % R
+    x3_cons = (x1y2 + y1x2 - (x3 + x3 * t)) * kappa
+    y3_cons = (y1y2 + x1x2 - (y3 - y3 * t)) * kappa * kappa
+    return (xy_cons + x3_cons + y3_cons) % R * sep % R
+
+
 # ============================================================================= prover
 def prove(comp, pk, ck, transcript):
     """Prover::prove_with_preprocessed (SURVEY §3.3, App. B.3).  Returns (proof dict, 1040 proof bytes)."""
@@ -376,9 +552,9 @@ def prove(comp, pk, ck, transcript):
     # round 3
     alpha = t.challenge_scalar(b"alpha")
     range_sep = t.challenge_scalar(b"range separation challenge")
-    t.challenge_scalar(b"logic separation challenge")
-    t.challenge_scalar(b"fixed base separation challenge")
-    t.challenge_scalar(b"variable base separation challenge")
+    logic_sep = t.challenge_scalar(b"logic separation challenge")
+    fixed_sep = t.challenge_scalar(b"fixed base separation challenge")
+    var_sep = t.challenge_scalar(b"variable base separation challenge")
     pi_dense = [comp.pi.get(i, 0) for i in range(n)]
     pi_poly = ifft(pi_dense, d)
     N4 = 4 * n
@@ -395,6 +571,14 @@ def prove(comp, pk, ck, transcript):
         gate = q4["q_arith"][i] * (q4["q_m"][i] * a * b + q4["q_l"][i] * a + q4["q_r"][i] * b + q4["q_o"][i] * c
                                    + q4["q_4"][i] * dd + q4["q_c"][i])
         gate += q4["q_range"][i] * _range_term(a, b, c, dd, d_next, range_sep)
+        a_next, b_next = w4[0][(i + 4) % N4], w4[1][(i + 4) % N4]
+        if q4["q_logic"][i]:
+            gate += q4["q_logic"][i] * _logic_term(a, a_next, b, b_next, c, dd, d_next, q4["q_c"][i], logic_sep)
+        if q4["q_fixed_group_add"][i]:
+            gate += q4["q_fixed_group_add"][i] * _fixed_base_term(a, a_next, b, b_next, c, dd, d_next, q4["q_l"][i], q4["q_r"][i],
+                                                                  q4["q_c"][i], fixed_sep)
+        if q4["q_variable_group_add"][i]:
+            gate += q4["q_variable_group_add"][i] * _var_base_term(a, a_next, b, b_next, c, dd, d_next, var_sep)
         gate += pi4[i]
         x = x4[i]
         ident = ((a + beta * x + gamma) * (b + beta * K1 * x + gamma) % R) * ((c + beta * K2 * x + gamma)
@@ -421,7 +605,7 @@ def prove(comp, pk, ck, transcript):
     ev["q_r_eval"] = poly_eval(pk["q_poly"]["q_r"], z)
     ev["perm_eval"] = poly_eval(z_poly, zw)
     t_eval = poly_eval(t_poly, z)
-    lin = linearisation_terms(ev, alpha, beta, gamma, range_sep, z, d)
+    lin = linearisation_terms(ev, alpha, beta, gamma, (range_sep, logic_sep, fixed_sep, var_sep), z, d)
     lin_poly = [0] * n
     for name, coef in lin["q"].items():
         for j, c in enumerate(pk["q_poly"][name]):
@@ -456,13 +640,19 @@ EVAL_BYTES_ORDER = ["a_eval", "b_eval", "c_eval", "d_eval", "a_next_eval", "b_ne
                     "lin_poly_eval", "perm_eval"]
 
 
-def linearisation_terms(ev, alpha, beta, gamma, range_sep, z, d):
+def linearisation_terms(ev, alpha, beta, gamma, seps, z, d):
     """Scalar coefficient of every polynomial (prover) / commitment (verifier) in the linearisation
-    r(X) — shared by `prove` and `verify` exactly as dusk-plonk's widgets share their formulas."""
+    r(X) — shared by `prove` and `verify` exactly as dusk-plonk's widgets share their formulas.
+    seps = (range, logic, fixed base, variable base) separation challenges."""
+    range_sep, logic_sep, fixed_sep, var_sep = seps
     a, b, c, dd = ev["a_eval"], ev["b_eval"], ev["c_eval"], ev["d_eval"]
+    an, bn, dn = ev["a_next_eval"], ev["b_next_eval"], ev["d_next_eval"]
     qa = ev["q_arith_eval"]
     q = {"q_m": a * b % R * qa % R, "q_l": a * qa % R, "q_r": b * qa % R, "q_o": c * qa % R, "q_4": dd * qa % R,
-         "q_c": qa, "q_range": _range_term(a, b, c, dd, ev["d_next_eval"], range_sep)}
+         "q_c": qa, "q_range": _range_term(a, b, c, dd, dn, range_sep),
+         "q_logic": _logic_term(a, an, b, bn, c, dd, dn, ev["q_c_eval"], logic_sep),
+         "q_fixed_group_add": _fixed_base_term(a, an, b, bn, c, dd, dn, ev["q_l_eval"], ev["q_r_eval"], ev["q_c_eval"], fixed_sep),
+         "q_variable_group_add": _var_base_term(a, an, b, bn, c, dd, dn, var_sep)}
     n = d["size"]
     z_h = (pow(z, n, R) - 1) % R
     l1 = z_h * pow(n * (z - 1) % R, -1, R) % R
@@ -684,13 +874,13 @@ def verify(vk, proof_bytes, pub_inputs, opening_key, label):
     t.append_commitment(b"z", pr["z_comm"])
     alpha = t.challenge_scalar(b"alpha")
     range_sep = t.challenge_scalar(b"range separation challenge")
-    t.challenge_scalar(b"logic separation challenge")
-    t.challenge_scalar(b"fixed base separation challenge")
-    t.challenge_scalar(b"variable base separation challenge")
+    logic_sep = t.challenge_scalar(b"logic separation challenge")
+    fixed_sep = t.challenge_scalar(b"fixed base separation challenge")
+    var_sep = t.challenge_scalar(b"variable base separation challenge")
     for lab, c in zip((b"t_1", b"t_2", b"t_3", b"t_4"), pr["t_comm"]):
         t.append_commitment(lab, c)
     z = t.challenge_scalar(b"z")
-    lin = linearisation_terms(ev, alpha, beta, gamma, range_sep, z, d)
+    lin = linearisation_terms(ev, alpha, beta, gamma, (range_sep, logic_sep, fixed_sep, var_sep), z, d)
     z_h, l1 = lin["z_h"], lin["l1"]
     if z_h == 0:
         return False

@@ -12,9 +12,9 @@
 // The NTTs and MSMs are the library's own hot path (ntt.cu, msm.cu).  The host keeps only the Fiat–Shamir
 // transcript (merlin.h) and a few dozen scalar operations per round (host_field.h).
 //
-// Supported widgets: arithmetic and range (q_arith·(q_m·a·b + q_l·a + q_r·b + q_o·c + q_4·d + q_c) + PI and the
-// q_range quad check).  A circuit with non-zero q_logic / q_fixed_group_add / q_variable_group_add columns is
-// rejected with PB200_ERR_ARG — there is no silent fallback.
+// Widgets: arithmetic (q_arith·(q_m·a·b + q_l·a + q_r·b + q_o·c + q_4·d + q_c) + PI), range (q_range quad check), and —
+// csrc/widgets.h — logic (XOR / AND quads), fixed-base scalar multiplication and variable-base point addition on JubJub,
+// i.e. every selector column StandardComposer has.
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
@@ -25,6 +25,7 @@
 #include "fr_vec.cuh"
 #include "host_field.h"
 #include "merlin.h"
+#include "widgets.h"
 
 using hostf::HFr;
 
@@ -208,6 +209,7 @@ struct QuotArgs {
     const Fr *zw, *dw;
     uint32_t dist, count, log_m, log_n1, row0;
     Fr alpha, alpha2, beta, gamma, range_sep;
+    Fr logic_sep, fixed_sep, var_sep, edwards_d;   // logic / fixed-base / variable-base widgets (EXTRA instantiation only)
     Fr vh_inv[4];        // 1 / ((7ω_4n^i)^n − 1) has period 4 in i
     KFactors ks;
 };
@@ -216,7 +218,8 @@ __device__ __forceinline__ Fr delta4(const Fr &f, const Fr &one) {  // f(f−1)(
     return (f * f1) * (f2 * f3);
 }
 __device__ __forceinline__ Fr quad(const Fr &x) { return x.dbl().dbl(); }
-template <bool RANGE>
+// EXTRA: the circuit has logic / fixed-base / variable-base rows (single-GPU layout only: they read a, b at index + 4)
+template <bool RANGE, bool EXTRA>
 __global__ void __launch_bounds__(128) quotient_kernel(const QuotArgs A) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= A.count) return;
@@ -244,6 +247,25 @@ __global__ void __launch_bounds__(128) quotient_kernel(const QuotArgs A) {
         r = r * kappa + delta4(b - quad(c), one);
         r = r * kappa + delta4(c - quad(d), one);
         g = g + (r * A.range_sep) * ld_fr(A.q[Q_RANGE] + i);
+    }
+    if (EXTRA) {
+        const Fr an = ld_fr(A.w + enext), bn = ld_fr(A.w + (size_t)ws + enext), dn = ld_fr(A.w + 3 * (size_t)ws + enext);
+        if (A.q[Q_LOGIC]) {
+            const Fr ql = ld_fr(A.q[Q_LOGIC] + i);
+            if (!ql.is_zero())
+                g = g + ql * widgets::logic_term(a, an, b, bn, c, d, dn, A.q[Q_C] ? ld_fr(A.q[Q_C] + i) : Fr::zero(), A.logic_sep);
+        }
+        if (A.q[Q_FIXED]) {
+            const Fr qf = ld_fr(A.q[Q_FIXED] + i);
+            if (!qf.is_zero())
+                g = g + qf * widgets::fixed_base_term(a, an, b, bn, c, d, dn, A.q[Q_L] ? ld_fr(A.q[Q_L] + i) : Fr::zero(),
+                                                      A.q[Q_R] ? ld_fr(A.q[Q_R] + i) : Fr::zero(),
+                                                      A.q[Q_C] ? ld_fr(A.q[Q_C] + i) : Fr::zero(), A.fixed_sep, A.edwards_d);
+        }
+        if (A.q[Q_VAR]) {
+            const Fr qv = ld_fr(A.q[Q_VAR] + i);
+            if (!qv.is_zero()) g = g + qv * widgets::var_base_term(a, an, b, bn, c, d, dn, A.var_sep, A.edwards_d);
+        }
     }
     g = g + ld_fr(A.pi + e);
     // permutation: identity part, copy part, L1 part
@@ -571,10 +593,6 @@ extern "C" int pb200_preprocess_sharded(pb200_ctx *ctx, const pb200_srs *srs, co
             for (size_t i = 0; i < 4 * ng && !nz; i++) nz = col[i] != 0;
         pk->q_nonzero[s] = nz;
     }
-    if (pk->q_nonzero[Q_LOGIC] || pk->q_nonzero[Q_FIXED] || pk->q_nonzero[Q_VAR]) {
-        pb_fail(ctx, PB200_ERR_ARG, "unsupported widget", "q_logic / q_fixed_group_add / q_variable_group_add must be zero", __FILE__, __LINE__);
-        return fail(PB200_ERR_ARG);
-    }
     // permutation: position (col, i) ↦ next occurrence of the same variable, cyclically, in gate order then l, r, o, 4
     std::vector<uint32_t> map(4 * n);
     {
@@ -782,9 +800,10 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
     // ---- round 3: quotient polynomial ------------------------------------------------------------------------------------
     const HFr alpha = tr.challenge_scalar("alpha");
     const HFr range_sep = tr.challenge_scalar("range separation challenge");
-    (void)tr.challenge_scalar("logic separation challenge");
-    (void)tr.challenge_scalar("fixed base separation challenge");
-    (void)tr.challenge_scalar("variable base separation challenge");
+    const HFr logic_sep = tr.challenge_scalar("logic separation challenge");
+    const HFr fixed_sep = tr.challenge_scalar("fixed base separation challenge");
+    const HFr var_sep = tr.challenge_scalar("variable base separation challenge");
+    const HFr edwards_d = (HFr::from_u64(10240) * HFr::from_u64(10241).inv()).neg();   // JubJub: −x² + y² = 1 + d·x²y²
     // dense public inputs → pi_poly
     PB_CUDA(ctx, cudaMemsetAsync(pk->pi_poly, 0, n * sizeof(Fr), st));
     if (n_pi) {
@@ -813,15 +832,21 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
     A.beta = to_dev(beta);
     A.gamma = to_dev(gamma);
     A.range_sep = to_dev(range_sep);
+    A.logic_sep = to_dev(logic_sep);
+    A.fixed_sep = to_dev(fixed_sep);
+    A.var_sep = to_dev(var_sep);
+    A.edwards_d = to_dev(edwards_d);
     for (int k = 0; k < 4; k++) A.vh_inv[k] = to_dev(pk->vh_inv[k]);
     A.ks = ks;
     A.zw = A.dw = nullptr;
     A.dist = A.log_m = A.log_n1 = A.row0 = 0;
     const bool range = pk->q_nonzero[Q_RANGE];
+    const bool extra = pk->q_nonzero[Q_LOGIC] || pk->q_nonzero[Q_FIXED] || pk->q_nonzero[Q_VAR];
     const uint32_t world = pk->shard.world, log_n4 = log_n + 2;
     uint32_t log_g = 0;
     while ((1u << log_g) < world) log_g++;
-    const bool dist3 = world > 1 && pk->shard.alltoall_dev && pk->shard.allgather_dev && log_n4 >= 8 + log_g + 2;
+    // (the sharded layout transforms z(ωX) and d(ωX) only: circuits with ECC / logic rows keep round 3 replicated)
+    const bool dist3 = world > 1 && pk->shard.alltoall_dev && pk->shard.allgather_dev && log_n4 >= 8 + log_g + 2 && !extra;
     if (!dist3) {
         // coset evaluations on 4n: a, b, c, d | z | pi   (L₁ is kept from preprocessing)
         Fr *w4 = pk->ev4, *z4 = pk->ev4 + 4 * N4, *pi4 = z4 + N4;
@@ -833,8 +858,13 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
         A.pi = pi4;
         A.out = pk->t_poly;
         A.count = (uint32_t)N4;
-        if (range) quotient_kernel<true><<<cdiv(N4, 128), 128, 0, st>>>(A);
-        else quotient_kernel<false><<<cdiv(N4, 128), 128, 0, st>>>(A);
+        if (extra) {
+            if (range) quotient_kernel<true, true><<<cdiv(N4, 128), 128, 0, st>>>(A);
+            else quotient_kernel<false, true><<<cdiv(N4, 128), 128, 0, st>>>(A);
+        } else {
+            if (range) quotient_kernel<true, false><<<cdiv(N4, 128), 128, 0, st>>>(A);
+            else quotient_kernel<false, false><<<cdiv(N4, 128), 128, 0, st>>>(A);
+        }
         PB_LAUNCHED(ctx);
         PB_TRY(pb200_ntt_dev(ctx, (uint64_t *)pk->t_poly, log_n4, 1, 1));
     } else {
@@ -921,8 +951,8 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
         A.log_m = log_m;
         A.log_n1 = log_n1;
         A.row0 = rank << log_rl;
-        if (range) quotient_kernel<true><<<cdiv(local, 128), 128, 0, st>>>(A);
-        else quotient_kernel<false><<<cdiv(local, 128), 128, 0, st>>>(A);
+        if (range) quotient_kernel<true, false><<<cdiv(local, 128), 128, 0, st>>>(A);
+        else quotient_kernel<false, false><<<cdiv(local, 128), 128, 0, st>>>(A);
         PB_LAUNCHED(ctx);
         // inverse: rows → regroup → all-to-all → columns (with n⁻¹ and the twiddles) → coset unscale
         PB_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)t_loc, log_m, rl, 1, 0));
@@ -1018,6 +1048,13 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
             r = r * kappa + delta(ev[E_C] - four * ev[E_D]);
             term(pk->q_poly[Q_RANGE], r * range_sep);
         }
+        if (pk->q_nonzero[Q_LOGIC])
+            term(pk->q_poly[Q_LOGIC], widgets::logic_term(ev[E_A], ev[E_AN], ev[E_B], ev[E_BN], ev[E_C], ev[E_D], ev[E_DN], ev[E_QC], logic_sep));
+        if (pk->q_nonzero[Q_FIXED])
+            term(pk->q_poly[Q_FIXED], widgets::fixed_base_term(ev[E_A], ev[E_AN], ev[E_B], ev[E_BN], ev[E_C], ev[E_D], ev[E_DN], ev[E_QL],
+                                                               ev[E_QR], ev[E_QC], fixed_sep, edwards_d));
+        if (pk->q_nonzero[Q_VAR])
+            term(pk->q_poly[Q_VAR], widgets::var_base_term(ev[E_A], ev[E_AN], ev[E_B], ev[E_BN], ev[E_C], ev[E_D], ev[E_DN], var_sep, edwards_d));
         term(pk->z_poly, lin_z);
         term(pk->sig_poly + 3 * n, lin_s4);
         A.terms = k;

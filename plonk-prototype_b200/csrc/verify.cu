@@ -20,6 +20,7 @@
 #include "../../include/pb200.h"
 #include "host_field.h"
 #include "merlin.h"
+#include "widgets.h"
 
 using hostf::HFp;
 using hostf::HFr;
@@ -375,9 +376,9 @@ extern "C" int pb200_verify(const uint8_t vk_commitments[15 * 48], size_t n, con
     tr.append_commitment("z", proof + 48 * P_Z);
     const HFr alpha = tr.challenge_scalar("alpha");
     const HFr range_sep = tr.challenge_scalar("range separation challenge");
-    (void)tr.challenge_scalar("logic separation challenge");
-    (void)tr.challenge_scalar("fixed base separation challenge");
-    (void)tr.challenge_scalar("variable base separation challenge");
+    const HFr logic_sep = tr.challenge_scalar("logic separation challenge");
+    const HFr fixed_sep = tr.challenge_scalar("fixed base separation challenge");
+    const HFr var_sep = tr.challenge_scalar("variable base separation challenge");
     const char *const tl[4] = {"t_1", "t_2", "t_3", "t_4"};
     for (int k = 0; k < 4; k++) tr.append_commitment(tl[k], proof + 48 * (P_T1 + k));
     const HFr z = tr.challenge_scalar("z");
@@ -434,9 +435,15 @@ extern "C" int pb200_verify(const uint8_t vk_commitments[15 * 48], size_t n, con
         rg = rg * kappa + delta(c - four * d);
         const HFr k1 = HFr::from_u64(7), k2 = HFr::from_u64(13), k3 = HFr::from_u64(17), bz = beta * z;
         const HFr id = (a + bz + gamma) * (b + k1 * bz + gamma) * (c + k2 * bz + gamma) * (d + k3 * bz + gamma);
-        const struct { int point; HFr s; } terms[9] = {{Q_M, a * b * qa}, {Q_L, a * qa}, {Q_R, b * qa}, {Q_O, c * qa}, {Q_4, d * qa},
-                                                       {Q_C, qa}, {Q_RANGE, rg * range_sep}, {-1, id * alpha + l1 * alpha2},
-                                                       {S4, (copy3 * beta * ev[E_PERM] * alpha).neg()}};
+        // logic / fixed-base / variable-base widgets: the same identities the prover's quotient uses, at the evaluations
+        const HFr edwards_d = (HFr::from_u64(10240) * HFr::from_u64(10241).inv()).neg();
+        const HFr lg = widgets::logic_term(a, ev[E_AN], b, ev[E_BN], c, d, ev[E_DN], ev[E_QC], logic_sep);
+        const HFr fx = widgets::fixed_base_term(a, ev[E_AN], b, ev[E_BN], c, d, ev[E_DN], ev[E_QL], ev[E_QR], ev[E_QC], fixed_sep, edwards_d);
+        const HFr vb = widgets::var_base_term(a, ev[E_AN], b, ev[E_BN], c, d, ev[E_DN], var_sep, edwards_d);
+        const struct { int point; HFr s; } terms[12] = {{Q_M, a * b * qa}, {Q_L, a * qa}, {Q_R, b * qa}, {Q_O, c * qa}, {Q_4, d * qa},
+                                                        {Q_C, qa}, {Q_RANGE, rg * range_sep}, {Q_LOGIC, lg}, {Q_FIXED, fx}, {Q_VAR, vb},
+                                                        {-1, id * alpha + l1 * alpha2},
+                                                        {S4, (copy3 * beta * ev[E_PERM] * alpha).neg()}};
         for (const auto &t : terms) r_comm = g1_add(r_comm, g1_mul(jac(t.point < 0 ? pr[P_Z] : vk[t.point]), t.s));
     }
     // the two aggregate openings

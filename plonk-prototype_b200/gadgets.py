@@ -9,10 +9,13 @@ would expect to carry over are kept on purpose: the decomposition allocates all 
 `min_bound` / `max_bound` pass a zero coefficient on the witness as their right operand, `max_bound` subtracts one from
 the bound first, and `bits_count` works on the canonical value starting from one.
 
-Not available: `commitment_gadget`, `MockCircuit::prove_ownership` and `check_hash_inputs` need the fixed-base /
-variable-base group-add widgets and dusk-poseidon's round constants, which this backend does not implement
-(pb200_preprocess rejects those selector columns) — they raise NotImplementedError rather than build a wrong circuit.
+`commitment_gadget` (gadgets.rs:28-41) and `MockCircuit::prove_ownership` (circuits.rs:63-66) go through the composer's
+`fixed_base_scalar_mul` / `point_addition_gate` / `assert_equal_public_point` and the GPU's fixed-base / variable-base
+widgets (csrc/widgets.h).  Not available: `check_hash_inputs` (circuits.rs:69-72) — dusk-poseidon's round constants and
+MDS matrix are generated data of a crate that is not on disk (Cargo.toml:23); it raises NotImplementedError rather than
+build a circuit with made-up constants.
 """
+from .jubjub import GENERATOR as GENERATOR_EXTENDED, GENERATOR_NUMS as GENERATOR_NUMS_EXTENDED
 from .prover import R
 
 
@@ -93,7 +96,10 @@ def range_check(composer, min_range, max_range, witness):
 
 
 def commitment_gadget(composer, value, blinder):
-    raise NotImplementedError("fixed_base_scalar_mul / point_addition_gate need the group-add widgets, which are not implemented")
+    """In-circuit Pedersen commitment value·G + blinder·G_nums (gadgets.rs:28-41); `value`, `blinder` are variables."""
+    p1 = composer.fixed_base_scalar_mul(value, GENERATOR_EXTENDED)
+    p2 = composer.fixed_base_scalar_mul(blinder, GENERATOR_NUMS_EXTENDED)
+    return composer.point_addition_gate(p1, p2)
 
 
 class MockCircuit:
@@ -106,7 +112,9 @@ class MockCircuit:
         return min_bound(composer, (tx_value + gas_fee) % R, self.note_value, 30)
 
     def prove_ownership(self, composer):
-        raise NotImplementedError("fixed_base_scalar_mul needs the fixed-base group-add widget, which is not implemented")
+        """Public-key ownership (circuits.rs:63-66): private_key·G computed in circuit equals the public key (public input)."""
+        circuit_pk = composer.fixed_base_scalar_mul(self.private_key, GENERATOR_EXTENDED)
+        composer.assert_equal_public_point(circuit_pk, self.public_key)
 
     def check_hash_inputs(self, composer, public_hash):
         raise NotImplementedError("dusk-poseidon's sponge gadget (round constants not available offline) is not implemented")

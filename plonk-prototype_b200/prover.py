@@ -45,8 +45,10 @@ class StandardComposer:
         self.variables.append(s % R)
         return len(self.variables) - 1
 
-    def _row(self, a, b, c, d, q_m=0, q_l=0, q_r=0, q_o=0, q_c=0, q_4=0, q_arith=1, q_range=0, pi=None):
-        row = dict(q_m=q_m, q_l=q_l, q_r=q_r, q_o=q_o, q_c=q_c, q_4=q_4, q_arith=q_arith, q_range=q_range)
+    def _row(self, a, b, c, d, q_m=0, q_l=0, q_r=0, q_o=0, q_c=0, q_4=0, q_arith=1, q_range=0, pi=None, q_logic=0,
+             q_fixed_group_add=0, q_variable_group_add=0):
+        row = dict(q_m=q_m, q_l=q_l, q_r=q_r, q_o=q_o, q_c=q_c, q_4=q_4, q_arith=q_arith, q_range=q_range, q_logic=q_logic,
+                   q_fixed_group_add=q_fixed_group_add, q_variable_group_add=q_variable_group_add)
         for k in SELECTORS:
             self.q[k].append(row.get(k, 0) % R)
         self.w_l.append(a)
@@ -99,6 +101,96 @@ class StandardComposer:
     def range_rows(self, a, b, c, d):
         """One row of the range widget (q_range = 1): quads c−4d, b−4c, a−4b, d_next−4a ∈ {0,1,2,3}."""
         self._row(a, b, c, d, q_arith=0, q_range=1)
+
+    def big_add_gate(self, a, b, c, d, q_l, q_r, q_o, q_4, q_c, pi=None):
+        self._row(a, b, c, self.zero_var if d is None else d, q_l=q_l, q_r=q_r, q_o=q_o, q_4=q_4, q_c=q_c, pi=pi)
+        return c
+
+    # ---- constraint_system::ecc — points are (x, y) pairs of variables on JubJub (plonk-prototype_b200/jubjub.py)
+    def fixed_base_scalar_mul(self, jubjub_scalar, generator):
+        """`fixed_base_scalar_mul(scalar, generator) -> Point` (/root/reference/src/zk/gadgets.rs:34,37; circuits.rs:64):
+        a 256-step ladder over the 2-bit windowed NAF of the scalar, most significant digit first.  Row i holds the point
+        accumulator (w_l, w_r), x_α·y_α of the point added (w_o) and the scalar accumulator (w_4), with the generator
+        multiple 2^(255−i)·G in q_l, q_r, q_c and q_fixed_group_add = 1; one plain row carries the final accumulators."""
+        from . import jubjub as jj
+        num_bits = 256
+        multiples = [tuple(generator)]
+        for _ in range(num_bits - 1):
+            multiples.append(jj.add(multiples[-1], multiples[-1]))
+        multiples.reverse()
+        k = self.variables[jubjub_scalar]
+        if k >= jj.JJ_ORDER:
+            raise ValueError("fixed_base_scalar_mul: the scalar is not a canonical JubJub scalar")  # JubJubScalar::from_bytes(..).unwrap()
+        scalar_acc, point_acc, xy_alphas = [0], [jj.IDENTITY], []
+        for i, entry in enumerate(reversed(jj.wnaf2(k))):
+            to_add = jj.IDENTITY if entry == 0 else (multiples[i] if entry == 1 else jj.neg(multiples[i]))
+            scalar_acc.append((2 * scalar_acc[i] + entry) % R)
+            point_acc.append(jj.add(point_acc[i], to_add))
+            xy_alphas.append(to_add[0] * to_add[1] % R)
+        for i in range(num_bits):
+            acc_x, acc_y = self.add_input(point_acc[i][0]), self.add_input(point_acc[i][1])
+            accumulated_bit = self.add_input(scalar_acc[i])
+            if i == 0:
+                self.constrain_to_constant(acc_x, 0, None)
+                self.constrain_to_constant(acc_y, 1, None)
+                self.constrain_to_constant(accumulated_bit, 0, None)
+            x_beta, y_beta = multiples[i]
+            xy_alpha = self.add_input(xy_alphas[i])
+            self._row(acc_x, acc_y, xy_alpha, accumulated_bit, q_l=x_beta, q_r=y_beta, q_c=x_beta * y_beta, q_arith=0,
+                      q_fixed_group_add=1)
+        acc_x, acc_y = self.add_input(point_acc[num_bits][0]), self.add_input(point_acc[num_bits][1])
+        last_accumulated_bit = self.add_input(scalar_acc[num_bits])
+        self.big_add_gate(acc_x, acc_y, self.zero_var, last_accumulated_bit, 0, 0, 0, 0, 0, None)
+        self.assert_equal(last_accumulated_bit, jubjub_scalar)
+        return (acc_x, acc_y)
+
+    def point_addition_gate(self, point_a, point_b):
+        """`point_addition_gate(p1, p2) -> Point` (/root/reference/src/zk/gadgets.rs:40): two rows, the first with
+        q_variable_group_add = 1 holding (x1, y1, x2, y2), the second (x3, y3, 0, x1·y2)."""
+        from . import jubjub as jj
+        (x1, y1), (x2, y2) = point_a, point_b
+        v = self.variables
+        x3v, y3v = jj.add((v[x1], v[y1]), (v[x2], v[y2]))
+        x1_y2 = self.add_input(v[x1] * v[y2])
+        x3, y3 = self.add_input(x3v), self.add_input(y3v)
+        self._row(x1, y1, x2, y2, q_arith=0, q_variable_group_add=1)
+        self._row(x3, y3, self.zero_var, x1_y2, q_arith=0)
+        return (x3, y3)
+
+    def assert_equal_public_point(self, point, public_point):
+        """`assert_equal_public_point` (/root/reference/src/zk/circuits.rs:65): two public-input constraints."""
+        self.constrain_to_constant(point[0], 0, -public_point[0])
+        self.constrain_to_constant(point[1], 0, -public_point[1])
+
+    # ---- constraint_system::logic — XOR / AND of two num_bits-bit variables, one 2-bit quad per row from the top
+    def _logic_gate(self, a, b, num_bits, is_xor):
+        assert num_bits % 2 == 0
+        av, bv = self.variables[a], self.variables[b]
+        nq, sel = num_bits // 2, (-1 if is_xor else 1)
+        rows_l, rows_r, rows_4, rows_o = [self.zero_var], [self.zero_var], [self.zero_var], []
+        la = ra = oa = 0
+        for i in range(nq):
+            sh = 2 * (nq - 1 - i)
+            lq, rq = (av >> sh) & 3, (bv >> sh) & 3
+            oq = (lq ^ rq) if is_xor else (lq & rq)
+            la, ra, oa = 4 * la + lq, 4 * ra + rq, 4 * oa + oq
+            rows_l.append(self.add_input(la))
+            rows_r.append(self.add_input(ra))
+            rows_4.append(self.add_input(oa))
+            rows_o.append(self.add_input(lq * rq))
+        rows_o.append(self.zero_var)
+        for i in range(nq + 1):
+            last = i == nq
+            self._row(rows_l[i], rows_r[i], rows_o[i], rows_4[i], q_arith=0, q_c=0 if last else sel, q_logic=0 if last else sel)
+        self.assert_equal(a, rows_l[nq])
+        self.assert_equal(b, rows_r[nq])
+        return rows_4[nq]
+
+    def xor_gate(self, a, b, num_bits):
+        return self._logic_gate(a, b, num_bits, True)
+
+    def and_gate(self, a, b, num_bits):
+        return self._logic_gate(a, b, num_bits, False)
 
     def add_dummy_constraints(self):
         six, one, seven, m20 = (self.add_input(v) for v in (6, 1, 7, -20))

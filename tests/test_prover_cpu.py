@@ -280,4 +280,40 @@ def test_reference_gadget_semantics_on_the_composer_mirror():
     cs3 = pb.StandardComposer()
     assert cs3.variables[G.range_check(cs3, 100, 1000, G.AllocatedScalar.allocate(cs3, 1000))] == 0   # max is exclusive
     with pytest.raises(NotImplementedError):
-        G.commitment_gadget(cs3, 0, 0)
+        G.MockCircuit(None, hash_inputs=[0]).check_hash_inputs(cs3, 0)      # dusk-poseidon's constants are not on disk
+
+
+def test_reference_ecc_gadgets_on_the_composer_mirror():
+    """gadgets.rs:28-41 `commitment_gadget` and circuits.rs:63-66 `prove_ownership` through the shipped composer mirror:
+    same rows as the protocol model's composer, the committed point is value·G + blinder·G_nums, all rows satisfied."""
+    import plonk_prototype_b200 as pb
+    G, jj = pb.gadgets, pb.jubjub
+    value, blinder = 0xC0FFEE, 0xB200B200B200
+    cs = pb.StandardComposer()
+    point = G.commitment_gadget(cs, cs.add_input(value), cs.add_input(blinder))
+    assert (cs.variables[point[0]], cs.variables[point[1]]) == jj.add(jj.mul(jj.GENERATOR, value), jj.mul(jj.GENERATOR_NUMS, blinder))
+    m = pm.Composer()
+    mv, mb = m.add_input(value), m.add_input(blinder)
+    mp = m.point_addition_gate(m.fixed_base_scalar_mul(mv, pm.JJ_GENERATOR), m.fixed_base_scalar_mul(mb, pm.JJ_GENERATOR_NUMS))
+    assert mp == point and cs.n == m.n == 3 + 2 * 261 + 2 and cs.variables == m.values
+    assert [list(x) for x in (cs.w_l, cs.w_r, cs.w_o, cs.w_4)] == m.w
+    for k in pm.SELECTORS:
+        assert cs.q[k] == m.q[k], k
+    assert m.check()
+    sk = 0x1234567
+    c2 = pb.StandardComposer()
+    G.MockCircuit(None, private_key=c2.add_input(sk), public_key=jj.mul(jj.GENERATOR, sk)).prove_ownership(c2)
+    assert c2.n == 3 + 261 + 2 and sorted(c2.public_inputs_sparse_store) == [c2.n - 2, c2.n - 1]
+    c_bad = pb.StandardComposer()
+    with pytest.raises(ValueError):                                         # JubJubScalar::from_bytes(..).unwrap() upstream
+        c_bad.fixed_base_scalar_mul(c_bad.add_input(jj.JJ_ORDER), jj.GENERATOR)
+    # logic gates: same rows as the model, right outputs
+    c3, m3 = pb.StandardComposer(), pm.Composer()
+    x = c3.xor_gate(c3.add_input(0xB5C3), c3.add_input(0x6F1A), 16)
+    y = c3.and_gate(c3.add_input(0xB5C3), c3.add_input(0x6F1A), 16)
+    m3.xor_gate(m3.add_input(0xB5C3), m3.add_input(0x6F1A), 16)
+    m3.and_gate(m3.add_input(0xB5C3), m3.add_input(0x6F1A), 16)
+    assert c3.variables[x] == 0xB5C3 ^ 0x6F1A and c3.variables[y] == 0xB5C3 & 0x6F1A
+    assert c3.variables == m3.values and [list(w) for w in (c3.w_l, c3.w_r, c3.w_o, c3.w_4)] == m3.w and m3.check()
+    for k in pm.SELECTORS:
+        assert c3.q[k] == m3.q[k], k
