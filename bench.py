@@ -221,7 +221,7 @@ def run_reference(args, rank, world):
 class ProveSetup:
     """Circuit, commit key, preprocessed prover key, witness in pinned host memory and in HBM."""
 
-    def __init__(self, ctx, L, torch, shard=None, dist=None, device=None):
+    def __init__(self, ctx, L, torch, shard=None, dist=None, device=None, lib_collectives=True):
         import plonk_prototype_b200 as pb
         from plonk_prototype_b200.synth import synthetic_circuit_columns
         self.ctx, self.L, self.n = ctx, L, 1 << L
@@ -239,8 +239,11 @@ class ProveSetup:
         else:
             rank, world = shard
             self.pp = pb.ShardedParameters(self.n, self.tau, rank, world, ctx)
-            self.pk, self.vk = ctx.preprocess(self.pp.srs, sel, wires, values.shape[0], LABEL,
-                                              shard=(rank, world, pb.torch_allgather(dist, device)) + pb.torch_device_collectives(dist, device))
+            if lib_collectives:   # every collective is the library's own NCCL call on its stream (pb200_comm)
+                self.pk, self.vk = ctx.preprocess_comm(self.pp.srs, sel, wires, values.shape[0], LABEL)
+            else:                 # host-language callbacks (torch.distributed), as a Python host without pb200_comm would
+                self.pk, self.vk = ctx.preprocess(self.pp.srs, sel, wires, values.shape[0], LABEL,
+                                                  shard=(rank, world, pb.torch_allgather(dist, device)) + pb.torch_device_collectives(dist, device))
         ctx.sync()
         self.setup_ms = 1e3 * (time.perf_counter() - t0)
         self.values_dev = ctx.malloc(values.nbytes)
@@ -357,7 +360,10 @@ def run_ours(args, rank, world, local_rank):
     cores = os.cpu_count() or 1
     imad_peak, _ = ctx.imad_peak()
 
-    setup = ProveSetup(ctx, L, torch, shard=(rank, world) if world > 1 else None, dist=dist, device=device)
+    lib_coll = args.collectives == "lib"
+    if world > 1 and lib_coll:
+        ctx.comm_init_from_torch(dist)   # torch.distributed only carries the 128-byte NCCL id
+    setup = ProveSetup(ctx, L, torch, shard=(rank, world) if world > 1 else None, dist=dist, device=device, lib_collectives=lib_coll)
     timed = timed_proves(setup, args, torch, stream, dist, device)
     proof = next(iter(timed["proofs"]))
     parity = {"deterministic": len(timed["proofs"]) == 1, "verifier_accepts": bool(setup.verify(proof)) if rank == 0 else None}
@@ -446,7 +452,8 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": timed["launches"], "clocks": timed["clocks"], "parity": parity, "rounds_ms": timed["rounds_ms"],
             "wall_ms_per_step": timed["wall_dev_ms"], "hbm_peak_gbs": peaks.get("hbm_gbs"),
             "sharding": ("commitments by point range (commit-key slice per rank, 144-byte partial sums all-gathered); round 3 as sharded "
-                         "four-step transforms (peer stores over NVLink + one all-to-all back); rounds 1, 2, 4, 5 replicated") if world > 1 else "single GPU",
+                         "four-step transforms (peer stores over NVLink + one all-to-all back); rounds 1, 2, 4, 5 replicated; collectives: "
+                         + ("NCCL inside libpb200.so on the library's stream (pb200_comm)" if lib_coll else "torch.distributed callbacks")) if world > 1 else "single GPU",
         }
         line.update(extra)
         print(json.dumps(line), flush=True)
@@ -650,13 +657,32 @@ def bench_ntt_sharded(ctx, dist, rank, world, args, torch):
     ctx.d2h(fused_out, peers.mine.ptr)
     same = bool((fused_out == buf.cpu().numpy().view(np.uint64).reshape(-1, 4)).all())
     peers.close()
-    t = torch.tensor([nccl_ms, fused_ms, 0.0 if (ok and same) else 1.0], device="cuda", dtype=torch.float64)
+    # the same transform driven entirely by the library (pb200_ntt_sharded_dev: NCCL all-to-all on the library's stream)
+    lib_ms, lib_same = float("inf"), True
+    if args.collectives == "lib":
+        d_data, d_tmp = ctx.malloc(spec.local * 32), ctx.malloc(spec.local * 32)
+        ctx.h2d(d_data, shard)
+        ctx.ntt_sharded_dev(d_data, d_tmp, L, False)
+        lib_out = np.empty((spec.local, 4), np.uint64)
+        ctx.d2h(lib_out, d_data)
+        lib_same = bool((lib_out == fused_out).all())
+        for _ in range(3):
+            ctx.ntt_sharded_dev(d_data, d_tmp, L, False)
+        dist.barrier(); ctx.sync()
+        e0.record(be.stream)
+        for _ in range(reps):
+            ctx.ntt_sharded_dev(d_data, d_tmp, L, False)
+        e1.record(be.stream)
+        ctx.sync(); dist.barrier()
+        lib_ms = e0.elapsed_time(e1) / reps
+        ctx.free(d_data); ctx.free(d_tmp)
+    t = torch.tensor([nccl_ms, fused_ms, 0.0 if (ok and same and lib_same) else 1.0, lib_ms], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    nccl_ms, fused_ms, bad = t.tolist()
-    ms = min(nccl_ms, fused_ms)
+    nccl_ms, fused_ms, bad, lib_ms = t.tolist()
+    ms = min(nccl_ms, fused_ms, lib_ms)
     return {"metric": "sharded four-step NTT, 2^%d points over %d GPUs (forward)" % (L, world), "ms": ms,
             "value": (1 << L) / (ms * 1e-3) / 1e6, "unit": "Melem/s", "scaling": "strong", "n1": spec.n1,
-            "fused_peer_store_ms": fused_ms, "nccl_all_to_all_ms": nccl_ms,
+            "fused_peer_store_ms": fused_ms, "nccl_all_to_all_ms": nccl_ms, "library_nccl_ms": lib_ms if lib_ms != float("inf") else None,
             "exchange_bytes_per_gpu": spec.local * 32 * (world - 1) // world,
             "verified": bad == 0.0, "roundtrip_ok": ok, "fused_equals_nccl": same,
             "note": "fused: column kernel writes the owners' row buffers over NVLink peer memory, wall clock incl. the cross-rank barrier; "
@@ -737,7 +763,7 @@ def bench_prove_large(ctx, args, torch, stream, dist=None, rank=0, world=1, devi
     """BASELINE.json configs[4]: the 2^24-gate synthetic circuit.  N = 1: one GPU (57 GiB prover key) — the baseline of the
     scaling curve.  N > 1: sharded prove; afterwards rank 0 proves the same circuit alone and the bytes must be equal."""
     L = args.large_log_gates
-    s = ProveSetup(ctx, L, torch, shard=(rank, world) if world > 1 else None, dist=dist, device=device)
+    s = ProveSetup(ctx, L, torch, shard=(rank, world) if world > 1 else None, dist=dist, device=device, lib_collectives=args.collectives == "lib")
     proofs = {s.prove_host() for _ in range(2)}
     reps = 3
     ctx.profile_enable(True)
@@ -800,6 +826,8 @@ def main():
     ap.add_argument("--skip-large", action="store_true", help="headline only: no MSM / NTT / 2^24-gate context objects")
     ap.add_argument("--skip-cpu", action="store_true", help="no CPU baseline legs (and no CPU byte-parity check)")
     ap.add_argument("--skip-single-check", action="store_true", help="N > 1: skip rank 0's single-GPU 2^24 proof")
+    ap.add_argument("--collectives", default="lib", choices=["lib", "torch"],
+                    help="N > 1: NCCL inside the library (pb200_comm) or torch.distributed callbacks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -202,12 +202,41 @@ typedef struct pb200_shard {
     void *user;
     pb200_alltoall_dev_fn alltoall_dev;   /* may be NULL: NTTs and the quotient kernel then run replicated */
     pb200_allgather_dev_fn allgather_dev; /* may be NULL */
+    uint32_t flags;                       /* PB200_SHARD_* */
 } pb200_shard;
+/* The device collectives are enqueued on the context's own stream (pb200_stream): the library then neither synchronises
+ * the stream before calling them nor assumes they have completed on return, and uses a stream-ordered collective as its
+ * cross-rank barrier.  Set by pb200_preprocess_comm; host-language callbacks that run on another stream leave it clear. */
+#define PB200_SHARD_STREAM_ORDERED 1u
 /* As pb200_preprocess, with `srs` holding this rank's slice.  The shard description is kept in the key: pb200_prove on a
  * sharded key must be given the same slice and is collective over all ranks. */
 PB200_API int pb200_preprocess_sharded(pb200_ctx *ctx, const pb200_srs *srs_slice, const pb200_circuit *circuit,
                                        const uint8_t *transcript_label, size_t label_len, const pb200_shard *shard,
                                        pb200_prover_key **out, uint8_t vk_commitments[15 * 48]);
+/* ---- multi-GPU communicator inside the library: one process per GPU, NCCL over NVLink / NVSwitch.
+ * Rank 0 obtains a 128-byte id (ncclUniqueId) and the host distributes it by any means; every rank then binds a
+ * communicator to its context.  All collectives below run on the context's stream.  NCCL is resolved at run time
+ * (libnccl.so.2 — the copy the host process already loaded, or the system's): PB200_ERR_NO_DEVICE when it cannot be. */
+PB200_API int pb200_comm_unique_id(unsigned char id_out[128]);
+PB200_API int pb200_comm_init(pb200_ctx *ctx, const unsigned char id[128], uint32_t rank, uint32_t world);
+PB200_API int pb200_comm_destroy(pb200_ctx *ctx);
+PB200_API int pb200_comm_info(const pb200_ctx *ctx, uint32_t *rank, uint32_t *world);
+/* recv_dev = world × bytes, rank-major | block h of send_dev → rank h, block b of recv_dev ← rank b.  Stream-ordered. */
+PB200_API int pb200_allgather_dev(pb200_ctx *ctx, const void *send_dev, void *recv_dev, size_t bytes);
+PB200_API int pb200_alltoall_dev(pb200_ctx *ctx, const void *send_dev, void *recv_dev, size_t bytes_per_peer);
+/* msm_variable_base over a point-range-sharded commit key: this rank's slice against its scalars, the
+ * 144-byte partial results all-gathered and summed; every rank receives the total.  Blocks; result on the host. */
+PB200_API int pb200_msm_g1_sharded_dev(pb200_ctx *ctx, const pb200_srs *srs_slice, size_t offset, const uint64_t *scalars_mont_dev, size_t n,
+                                       uint64_t out_xyz_mont[18]);
+/* EvaluationDomain::fft / ifft of ONE 2^log_n vector sharded over the communicator's ranks (domains ≥ 2^24):
+ * four-step, n = n1·m with n1 = 2^8.  Forward: `data` holds this rank's column-layout shard A[j1][c] = x[j1·m + rank·m/G + c]
+ * and receives its row-layout shard B[r][k'] = X[(rank·n1/G + r) + n1·k']; inverse: the way back (with n⁻¹).  `tmp`: a
+ * second buffer of 2^log_n / G scalars.  One all-to-all; stream-ordered, no host synchronisation. */
+PB200_API int pb200_ntt_sharded_dev(pb200_ctx *ctx, uint64_t *data_dev, uint64_t *tmp_dev, uint32_t log_n, int inverse);
+/* pb200_preprocess_sharded with the context's communicator supplying every collective (no host callbacks). */
+PB200_API int pb200_preprocess_comm(pb200_ctx *ctx, const pb200_srs *srs_slice, const pb200_circuit *circuit, const uint8_t *transcript_label,
+                                    size_t label_len, pb200_prover_key **out, uint8_t vk_commitments[15 * 48]);
+
 /* Prover::prove_with_preprocessed + Proof::to_bytes: the witness is the value of every variable (n_vars Montgomery
  * scalars, host), the public inputs a sparse (gate index, value) list.  Rounds 1-5 run on the device with the
  * polynomials resident between rounds; the host hashes the transcript.  proof_out: 11 compressed G1 + 16 scalars.

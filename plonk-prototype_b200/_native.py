@@ -26,6 +26,8 @@ EXPORTS = [
     "pb200_synthetic_bases_dev", "pb200_profile_enable", "pb200_profile_ms", "pb200_profile_reset", "pb200_profile_sum_ms",
     "pb200_launch_count",
     "pb200_imad_peak",
+    "pb200_comm_unique_id", "pb200_comm_init", "pb200_comm_destroy", "pb200_comm_info", "pb200_allgather_dev", "pb200_alltoall_dev",
+    "pb200_msm_g1_sharded_dev", "pb200_ntt_sharded_dev", "pb200_preprocess_comm",
 ]
 
 
@@ -40,7 +42,7 @@ DEV_COLLECTIVE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_voi
 class Shard(ctypes.Structure):
     """`pb200_shard` (include/pb200.h)."""
     _fields_ = [("rank", ctypes.c_uint32), ("world", ctypes.c_uint32), ("allgather", ALLGATHER_FN), ("user", ctypes.c_void_p),
-                ("alltoall_dev", DEV_COLLECTIVE_FN), ("allgather_dev", DEV_COLLECTIVE_FN)]
+                ("alltoall_dev", DEV_COLLECTIVE_FN), ("allgather_dev", DEV_COLLECTIVE_FN), ("flags", ctypes.c_uint32)]
 
 
 class Circuit(ctypes.Structure):
@@ -126,6 +128,15 @@ def lib():
         L.pb200_launch_count.argtypes = [vp]
         L.pb200_launch_count.restype = ctypes.c_uint64
         L.pb200_imad_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        L.pb200_comm_unique_id.argtypes = [ctypes.c_char_p]
+        L.pb200_comm_init.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32]
+        L.pb200_comm_destroy.argtypes = [vp]
+        L.pb200_comm_info.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
+        L.pb200_allgather_dev.argtypes = [vp, vp, vp, ctypes.c_size_t]
+        L.pb200_alltoall_dev.argtypes = [vp, vp, vp, ctypes.c_size_t]
+        L.pb200_msm_g1_sharded_dev.argtypes = [vp, vp, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]
+        L.pb200_ntt_sharded_dev.argtypes = [vp, u64p, u64p, ctypes.c_uint32, ctypes.c_int]
+        L.pb200_preprocess_comm.argtypes = [vp, vp, ctypes.POINTER(Circuit), ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(vp), vp]
         _lib = L
     return _lib
 
@@ -371,12 +382,70 @@ class Context:
 
         cb = ALLGATHER_FN(trampoline)
         dev_cbs = [dev_trampoline(f) if f is not None else DEV_COLLECTIVE_FN() for f in dev_fns]
-        sh = Shard(rank, world, cb, None, dev_cbs[0], dev_cbs[1])
+        sh = Shard(rank, world, cb, None, dev_cbs[0], dev_cbs[1], 0)
         self._check(lib().pb200_preprocess_sharded(self._h, srs, ctypes.byref(c), bytes(label), len(label), ctypes.byref(sh),
                                                    ctypes.byref(h), _ptr(vk)))
         if not hasattr(self, "_keepalive"):
             self._keepalive = {}
         self._keepalive[h.value] = (cb, dev_cbs)  # the key holds the function pointers for every later pb200_prove
+        return h, vk.tobytes()
+
+    # -- multi-GPU communicator inside the library (NCCL; csrc/comm.cu)
+    @staticmethod
+    def comm_unique_id():
+        buf = ctypes.create_string_buffer(128)
+        rc = lib().pb200_comm_unique_id(buf)
+        if rc != 0:
+            raise Pb200Error("pb200_comm_unique_id failed (%d): NCCL (libnccl.so.2) is not loadable in this process" % rc)
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, world):
+        self._check(lib().pb200_comm_init(self._h, bytes(unique_id), rank, world))
+
+    def comm_init_from_torch(self, dist):
+        """Bind the library's own NCCL communicator using torch.distributed only to broadcast the 128-byte id."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.comm_init(box[0], rank, world)
+
+    def comm_destroy(self):
+        self._check(lib().pb200_comm_destroy(self._h))
+
+    def allgather_dev(self, send_dev, recv_dev, nbytes):
+        self._check(lib().pb200_allgather_dev(self._h, ctypes.c_void_p(send_dev), ctypes.c_void_p(recv_dev), nbytes))
+
+    def alltoall_dev(self, send_dev, recv_dev, bytes_per_peer):
+        self._check(lib().pb200_alltoall_dev(self._h, ctypes.c_void_p(send_dev), ctypes.c_void_p(recv_dev), bytes_per_peer))
+
+    def msm_sharded_dev(self, srs_slice, scalars_dev, n, offset=0):
+        out = np.zeros(18, np.uint64)
+        self._check(lib().pb200_msm_g1_sharded_dev(self._h, srs_slice, offset, ctypes.c_void_p(scalars_dev), n, _ptr(out)))
+        return out
+
+    def ntt_sharded_dev(self, data_dev, tmp_dev, log_n, inverse=False):
+        self._check(lib().pb200_ntt_sharded_dev(self._h, ctypes.c_void_p(data_dev), ctypes.c_void_p(tmp_dev), log_n, int(inverse)))
+
+    def preprocess_comm(self, srs_slice, selectors, wires, n_vars, label):
+        """`pb200_preprocess_comm`: a sharded prover key whose collectives are the library's own NCCL calls."""
+        keep = []
+        c = Circuit()
+        c.n_gates = len(wires[0])
+        c.n_vars = n_vars
+        for k in range(11):
+            if selectors[k] is None:
+                c.selectors[k] = None
+            else:
+                a = np.ascontiguousarray(selectors[k], dtype=np.uint64).reshape(-1, 4)
+                keep.append(a)
+                c.selectors[k] = a.ctypes.data
+        for k in range(4):
+            a = np.ascontiguousarray(wires[k], dtype=np.uint32)
+            keep.append(a)
+            c.wires[k] = a.ctypes.data
+        h = ctypes.c_void_p()
+        vk = np.zeros(15 * 48, np.uint8)
+        self._check(lib().pb200_preprocess_comm(self._h, srs_slice, ctypes.byref(c), bytes(label), len(label), ctypes.byref(h), _ptr(vk)))
         return h, vk.tobytes()
 
     def prover_key_free(self, pk):

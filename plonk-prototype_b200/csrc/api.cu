@@ -52,6 +52,7 @@ extern "C" void pb200_destroy(pb200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    pb200_comm_destroy(ctx);
     ntt_free_plans(ctx);
     if (ctx->msm_ws) cudaFree(ctx->msm_ws);
     if (ctx->stage) cudaFree(ctx->stage);

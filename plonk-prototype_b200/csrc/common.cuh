@@ -10,7 +10,8 @@
 
 #include "../../include/pb200.h"
 
-struct NttPlan;  // ntt.cu
+struct NttPlan;     // ntt.cu
+struct pb200_comm;  // comm.cu: NCCL communicator of a multi-GPU context (nullptr = single GPU)
 
 struct pb200_ctx {
     int device = 0;
@@ -33,6 +34,7 @@ struct pb200_ctx {
     size_t stage_bytes = 0;
     void *pinned = nullptr;  // small pinned staging block for results
     size_t pinned_bytes = 0;
+    pb200_comm *comm = nullptr;
 };
 
 struct pb200_srs {
@@ -110,3 +112,5 @@ struct PbTimer {
 };
 
 int pb_ensure(pb200_ctx *ctx, void **buf, size_t *have, size_t need);  // api.cu
+int comm_allgather_host(pb200_ctx *ctx, const void *send, void *recv, size_t bytes);  // comm.cu
+int comm_stream_barrier(pb200_ctx *ctx);                                              // comm.cu

@@ -411,7 +411,7 @@ struct pb200_prover_key {
     uint8_t vk_bytes[15 * 48];
     merlin::Transcript *seeded = nullptr;
     // point-range sharding of the commitments (world = 1: none)
-    pb200_shard shard = {0, 1, nullptr, nullptr, nullptr, nullptr};
+    pb200_shard shard = {0, 1, nullptr, nullptr, nullptr, nullptr, 0};
     size_t slice_lo = 0, slice_n = 0;  // this rank's coefficient range [slice_lo, slice_lo + slice_n)
     // peer mappings of every rank's key slab (CUDA IPC over NVLink) for the fused column-transform + exchange kernel
     void *peer_slab[8] = {};
@@ -883,13 +883,16 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
                                                       {pk->w_poly + 3 * n, seven}, {pk->z_poly, seven}, {pk->pi_poly, seven},
                                                       {pk->z_poly, seven * pk->omega}, {pk->w_poly + 3 * n, seven * pk->omega}};
         const int n_src = range ? 8 : 7;
+        // in-library NCCL (pb200_preprocess_comm): collectives are enqueued on `st` itself — no host synchronisation anywhere
+        const bool ordered = (pk->shard.flags & PB200_SHARD_STREAM_ORDERED) != 0;
         auto exchange = [&](Fr *send, Fr *recv) -> int {
-            PB_CUDA(ctx, cudaStreamSynchronize(st));
+            if (!ordered) PB_CUDA(ctx, cudaStreamSynchronize(st));
             if (pk->shard.alltoall_dev(pk->shard.user, send, recv, peer_bytes) != 0)
-                return pb_fail(ctx, PB200_ERR_ARG, "sharded transform", "the all-to-all callback failed", __FILE__, __LINE__);
+                return ordered ? PB200_ERR_CUDA : pb_fail(ctx, PB200_ERR_ARG, "sharded transform", "the all-to-all callback failed", __FILE__, __LINE__);
             return 0;
         };
         auto barrier = [&]() -> int {  // every rank's stream has drained: a one-byte all-gather through the host collective
+            if (ordered) return comm_stream_barrier(ctx);   // … or, stream-ordered, a one-word NCCL all-gather on `st`
             PB_CUDA(ctx, cudaStreamSynchronize(st));
             uint8_t one_byte = 1, all[8];
             if (pk->shard.allgather(pk->shard.user, &one_byte, all, 1) != 0)
@@ -962,9 +965,9 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
         dist_unscale_kernel<<<cdiv(local / 4, 256), 256, 0, st>>>(t_loc, log_m, log_cl, col0, (uint32_t)local, to_dev(seven.inv()));
         PB_LAUNCHED(ctx);
         // every rank needs all of t(X) for rounds 4-5: all-gather the column shards, then back to natural order
-        PB_CUDA(ctx, cudaStreamSynchronize(st));
+        if (!ordered) PB_CUDA(ctx, cudaStreamSynchronize(st));
         if (pk->shard.allgather_dev(pk->shard.user, t_loc, gathered, local * sizeof(Fr)) != 0)
-            return pb_fail(ctx, PB200_ERR_ARG, "sharded transform", "the device all-gather callback failed", __FILE__, __LINE__);
+            return ordered ? PB200_ERR_CUDA : pb_fail(ctx, PB200_ERR_ARG, "sharded transform", "the device all-gather callback failed", __FILE__, __LINE__);
         PB_TRY(pb200_block_transpose_dev(ctx, (uint64_t *)pk->t_poly, (const uint64_t *)gathered, world, 1u << log_n1, cl));
     }
     const char *const t_label[4] = {"t_1", "t_2", "t_3", "t_4"};

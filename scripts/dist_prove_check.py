@@ -26,11 +26,17 @@ def main():
     gather = pb.torch_allgather(dist, dev)
     a2a_dev, ag_dev = pb.torch_device_collectives(dist, dev)
     replicate_round3 = bool(os.environ.get("PB200_REPLICATE_ROUND3"))
+    use_comm = os.environ.get("PB200_DIST_MODE", "comm") == "comm"   # collectives by the library's own NCCL communicator
+    if use_comm:
+        ctx.comm_init_from_torch(dist)
     for L in [int(a) for a in sys.argv[1:]] or [16]:
         n, tau, label = 1 << L, 0xB2000000 + L, b"pb200-dist"
         sel, wires, values, pi_pos, pi_vals = synthetic_circuit_columns(n)
         sp = pb.ShardedParameters(n, tau, rank, world, ctx)
-        pk, vk = ctx.preprocess(sp.srs, sel, wires, values.shape[0], label, shard=(rank, world, gather) if replicate_round3 else (rank, world, gather, a2a_dev, ag_dev))
+        if use_comm:
+            pk, vk = ctx.preprocess_comm(sp.srs, sel, wires, values.shape[0], label)
+        else:
+            pk, vk = ctx.preprocess(sp.srs, sel, wires, values.shape[0], label, shard=(rank, world, gather) if replicate_round3 else (rank, world, gather, a2a_dev, ag_dev))
         proof = ctx.prove(sp.srs, pk, values, pi_pos, pi_vals)
         t = []
         for _ in range(3):
@@ -62,7 +68,7 @@ def main():
         dist.barrier()
         if rank == 0:
             print(json.dumps({"log_gates": L, "world": world, "prove_ms": sum(t) / len(t), "min_ms": min(t),
-                              "round3": "replicated" if replicate_round3 else "sharded", "all_ranks_same_proof": same, "single_gpu_ms": single_ms, "equals_single_gpu_proof": matches,
+                              "round3": "replicated" if replicate_round3 else "sharded", "collectives": "library NCCL (pb200_comm)" if use_comm else "host callbacks (torch.distributed)", "all_ranks_same_proof": same, "single_gpu_ms": single_ms, "equals_single_gpu_proof": matches,
                               "proof_sha256": hashlib.sha256(proof).hexdigest()[:16]}), flush=True)
     ctx.close()
     dist.destroy_process_group()

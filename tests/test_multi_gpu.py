@@ -32,16 +32,21 @@ def test_sharded_ntt_equals_single_gpu_transform():
     world = _world()
     for log_n in (20, 24):
         out = _torchrun(world, "dist_ntt_check.py", log_n)
-        fused, nccl = out[-2], out[-1]
+        lib, fused, nccl = out[-3], out[-2], out[-1]
+        assert lib["matches_single_gpu"] is True and lib["ifft_roundtrip"] is True and lib["sharded_msm_equals_single_gpu"] is True
         assert nccl["log_n"] == log_n and nccl["n_gpus"] == world
         assert nccl["all_shards_match_single_gpu"] is True and nccl["ifft_roundtrip"] is True
         assert fused["fused_matches_single_gpu"] is True
 
 
-@pytest.mark.parametrize("mode", ["fused", "nccl"])
+@pytest.mark.parametrize("mode", ["comm-fused", "comm-nccl", "callbacks-fused", "callbacks-nccl"])
 def test_sharded_prove_equals_single_gpu_proof(mode):
+    """comm: every collective by the library's own NCCL communicator (pb200_preprocess_comm), stream-ordered; callbacks: through the
+    host's torch.distributed callbacks.  fused: round-3 forward exchange as peer stores; nccl: as an all-to-all."""
     world = _world()
-    env = {"PB200_ROUND3_NCCL": "1"} if mode == "nccl" else {}
+    env = {"PB200_DIST_MODE": mode.split("-")[0]}
+    if mode.endswith("nccl"):
+        env["PB200_ROUND3_NCCL"] = "1"
     out = _torchrun(world, "dist_prove_check.py", 12, 16, 20, env=env)
     assert [o["log_gates"] for o in out] == [12, 16, 20]
     for o in out:
