@@ -174,6 +174,23 @@ int comm_stream_barrier(pb200_ctx *ctx) {
     return 0;
 }
 
+// The sharded prover's commitments: every rank leaves its `batch` partial MSM results (36 words each) in the first 64 KiB of
+// the staging block; they are all-gathered, added per batch element by one kernel and copied to the host once — no
+// per-element round trips, no host collective.
+uint32_t *comm_partials_buffer(pb200_ctx *ctx) { return ctx->comm ? (uint32_t *)ctx->comm->small_dev : nullptr; }
+int comm_sum_partials(pb200_ctx *ctx, uint32_t batch, uint64_t *out_xyz_host) {
+    PB_ARG(ctx, ctx->comm != nullptr && batch >= 1 && (size_t)batch * 144 <= ((size_t)1 << 15));
+    pb200_comm *c = ctx->comm;
+    char *s = (char *)c->small_dev, *r = s + ((size_t)1 << 16);
+    uint32_t *sums = (uint32_t *)(s + ((size_t)1 << 15));   // upper half of the send block
+    PB_NCCL(ctx, nccl_api()->AllGather(s, r, (size_t)batch * 144, ncclUint8, c->comm, ctx->stream));
+    PB_TRY(tail_g1_sum_batch(ctx, (const uint32_t *)r, c->world, batch, sums));
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sums, (size_t)batch * 144, cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(out_xyz_host, ctx->pinned, (size_t)batch * 144);
+    return 0;
+}
+
 // ---- callbacks with the pb200_shard signatures, bound to a context's communicator (user = ctx) ------------------------------
 static int cb_allgather(void *user, const void *send, void *recv, size_t bytes) {
     return comm_allgather_host((pb200_ctx *)user, send, recv, bytes);

@@ -114,3 +114,11 @@ struct PbTimer {
 int pb_ensure(pb200_ctx *ctx, void **buf, size_t *have, size_t need);  // api.cu
 int comm_allgather_host(pb200_ctx *ctx, const void *send, void *recv, size_t bytes);  // comm.cu
 int comm_stream_barrier(pb200_ctx *ctx);                                              // comm.cu
+// Σ over ranks of `batch` projective points each rank holds in comm_partials_buffer(): all-gather + add on the device, one D2H
+uint32_t *comm_partials_buffer(pb200_ctx *ctx);                                       // comm.cu
+int comm_sum_partials(pb200_ctx *ctx, uint32_t batch, uint64_t *out_xyz_host);        // comm.cu
+// msm.cu: batched MSM over pre-doubled bases with the results left in device memory (36 words each)
+struct pb200_srs;
+int msm_batch_to_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_dev, size_t n, uint32_t batch,
+                     size_t scalar_stride, uint32_t *result_dev, bool *handled);
+int tail_g1_sum_batch(pb200_ctx *ctx, const uint32_t *pts, uint32_t count, uint32_t batch, uint32_t *results);  // msm_tail.cu

@@ -375,7 +375,7 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     } else {
         PB_TRY(tail_sum(ctx, n_win, 1, chunks, chunks_per_window, wsum));
     }
-    if (batch > 1) PB_TRY(tail_batch_results(ctx, wsum, batch, result_dev));
+    if (batch > 1 || (pre_stride && running_total == nullptr)) PB_TRY(tail_batch_results(ctx, wsum, batch, result_dev));
     else PB_TRY(tail_combine(ctx, wsum, rcfg, running_total, first, last, result_dev));
     t_red.stop();
     if (ctx->profile) {
@@ -457,6 +457,22 @@ static int msm_run(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const ui
     t_total.collect();
     memcpy(out_host, ctx->pinned, 36 * 4);
     return 0;
+}
+
+// Batched MSM over pre-doubled bases whose `batch` results (36 words each: projective X ‖ Y ‖ Z) stay in device memory, stream-
+// ordered, no host synchronisation — for the sharded prover, which all-gathers and adds the ranks' partial sums on the device
+// before anything returns to the host.  *handled = false (and nothing launched) when the pre-doubled path does not apply.
+int msm_batch_to_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_dev, size_t n, uint32_t batch,
+                     size_t scalar_stride, uint32_t *result_dev, bool *handled) {
+    *handled = false;
+    const bool pre_ok = srs != nullptr && srs->pre != nullptr && n > 0 && n * 16 >= srs->n && (uint64_t)srs->W_pre * srs->n < (1ull << 31) &&
+                        (uint64_t)n * srs->W_pre * batch < (1ull << 32) && n <= ((size_t)1 << 26) && batch >= 1 && batch <= 64 &&
+                        offset <= srs->n && n <= srs->n - offset && (batch == 1 || scalar_stride >= n);
+    if (!pre_ok) return 0;
+    *handled = true;
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const G1Affine *bases = reinterpret_cast<const G1Affine *>(srs->pre) + offset;
+    return msm_piece(ctx, bases, scalars_dev, (uint32_t)n, 1, 1, nullptr, result_dev, srs->c_pre, (uint32_t)srs->n, batch, (uint32_t)scalar_stride);
 }
 
 extern "C" int pb200_srs_upload(pb200_ctx *ctx, const uint64_t *xy_mont_host, size_t n_points, pb200_srs **out) {

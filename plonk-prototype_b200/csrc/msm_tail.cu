@@ -147,6 +147,27 @@ __global__ void g1_sum_kernel(const uint32_t *pts, uint32_t count, uint32_t *res
     write_projective(total, result);
 }
 
+// Thread j adds record j of every rank's block: pts = [count][batch] records of 36 words (projective X ‖ Y ‖ Z) as an
+// all-gather of the ranks' batched MSM results delivers them; results[j] = Σ_r pts[r][j].
+__global__ void g1_sum_batch_kernel(const uint32_t *pts, uint32_t count, uint32_t batch, uint32_t *results) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= batch) return;
+    G1Xyzz total = G1Xyzz::identity();
+    for (uint32_t r = 0; r < count; r++) {
+        const uint32_t *q = pts + 36 * ((size_t)r * batch + j);
+        Fp X, Y, Z;
+        for (int k = 0; k < 12; k++) { X.l[k] = q[k]; Y.l[k] = q[12 + k]; Z.l[k] = q[24 + k]; }
+        if (Z.is_zero()) continue;
+        G1Xyzz p;
+        p.zz = Z.sqr();
+        p.zzz = p.zz * Z;
+        p.x = X * Z;
+        p.y = Y * p.zz;
+        total = g1_add(total, p);
+    }
+    write_projective(total, results + 36 * j);
+}
+
 // ------------------------------------------------------------------------------ synthetic bases
 // bases[i] = (a + i·d)·G; each thread walks `per` consecutive points by repeated addition of d·G.
 __global__ void __launch_bounds__(128) synthetic_bases_kernel(G1Affine *out, uint64_t n, uint64_t a, uint64_t d, uint32_t per) {
@@ -226,6 +247,11 @@ int tail_batch_results(pb200_ctx *ctx, const G1Xyzz *set_sums, uint32_t batch, u
 }
 int tail_g1_sum(pb200_ctx *ctx, const uint32_t *pts, uint32_t count, uint32_t *result) {
     g1_sum_kernel<<<1, 1, 0, ctx->stream>>>(pts, count, result);
+    PB_LAUNCHED(ctx);
+    return 0;
+}
+int tail_g1_sum_batch(pb200_ctx *ctx, const uint32_t *pts, uint32_t count, uint32_t batch, uint32_t *results) {
+    g1_sum_batch_kernel<<<(batch + 31) / 32, 32, 0, ctx->stream>>>(pts, count, batch, results);
     PB_LAUNCHED(ctx);
     return 0;
 }

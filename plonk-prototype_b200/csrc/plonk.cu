@@ -498,6 +498,17 @@ int commit_bytes_batch(pb200_ctx *ctx, const pb200_srs *srs, const pb200_prover_
         PB_TRY(pb200_msm_g1_batch_dev(ctx, srs, 0, (const uint64_t *)polys, n, batch, stride, xyz));
     } else {
         PB_ARG(ctx, n == pk->n);
+        if ((pk->shard.flags & PB200_SHARD_STREAM_ORDERED) && comm_partials_buffer(ctx)) {
+            // in-library NCCL: partial sums stay on the device — MSM → all-gather → one add kernel → one D2H
+            bool handled = false;
+            PB_TRY(msm_batch_to_dev(ctx, srs, 0, (const uint64_t *)(polys + pk->slice_lo), pk->slice_n, batch, stride, comm_partials_buffer(ctx),
+                                    &handled));
+            if (handled) {
+                PB_TRY(comm_sum_partials(ctx, batch, xyz));
+                for (uint32_t j = 0; j < batch; j++) hostf::g1_projective_to_bytes(xyz + 18 * j, out + 48 * j);
+                return 0;
+            }
+        }
         PB_TRY(pb200_msm_g1_batch_dev(ctx, srs, 0, (const uint64_t *)(polys + pk->slice_lo), pk->slice_n, batch, stride, xyz));
         const uint32_t world = pk->shard.world;
         std::vector<uint64_t> all((size_t)world * batch * 18), one((size_t)world * 18);
