@@ -339,7 +339,8 @@ constexpr int kMaxJobs = 20;
 constexpr uint32_t kEvalPerThread = 8, kEvalTile = 256 * kEvalPerThread;
 struct EvalArgs {
     const Fr *p[kMaxJobs];
-    uint32_t len[kMaxJobs];
+    uint32_t len[kMaxJobs];    // coefficients this launch covers: [off, off + len)
+    uint32_t off[kMaxJobs];    // (a rank of a sharded prove evaluates its coefficient slice; the partial sums are all-gathered)
     uint32_t point[kMaxJobs];
     Fr points[2];
     Fr *partial;  // [job][tiles]
@@ -362,7 +363,11 @@ __global__ void __launch_bounds__(256) poly_eval_partial_kernel(const EvalArgs A
     __shared__ uint4 smraw[512];
     Fr *sm = reinterpret_cast<Fr *>(smraw);
     const uint32_t job = blockIdx.y, len = A.len[job];
-    const Fr *p = A.p[job];
+    if (blockIdx.x * kEvalTile >= len) {   // short job in a grid sized for the longest one: nothing to add
+        if (threadIdx.x == 0) st_fr(A.partial + (size_t)job * A.tiles + blockIdx.x, Fr::zero());
+        return;
+    }
+    const Fr *p = A.p[job] + A.off[job];
     const Fr x = A.points[A.point[job]];
     const uint32_t first = blockIdx.x * kEvalTile + threadIdx.x * kEvalPerThread;
     Fr acc = Fr::zero();
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(256) poly_eval_partial_kernel(const EvalArgs A
         const uint32_t last = min(first + kEvalPerThread, len);
         acc = ld_fr(p + last - 1);
         for (uint32_t j = last - 1; j-- > first;) acc = acc * x + ld_fr(p + j);
-        acc = acc * x.pow_u32(first);
+        acc = acc * x.pow_u32(A.off[job] + first);
     }
     acc = block_sum(acc, sm);
     if (threadIdx.x == 0) st_fr(A.partial + (size_t)job * A.tiles + blockIdx.x, acc);
@@ -531,6 +536,25 @@ int coset_extend(pb200_ctx *ctx, Fr *dst, const Fr *src, uint32_t n, uint32_t lo
     pad_copy_kernel<<<dim3(cdiv(N4, 256), batch), 256, 0, ctx->stream>>>(dst, src, n, N4);
     PB_LAUNCHED(ctx);
     return pb200_ntt_batch_dev(ctx, (uint64_t *)dst, log_n4, batch, 0, 1);
+}
+
+// Σ over the ranks of `count` scalars each rank computed from its slice (evaluation partial sums): one host all-gather
+// (count × 32 bytes per rank) and `world` exact field additions — every rank derives the same values.  world = 1: a copy.
+int sum_over_ranks(pb200_ctx *ctx, const pb200_prover_key *pk, const uint64_t *mine, int count, HFr *out) {
+    const uint32_t world = pk->shard.world;
+    if (world <= 1) {
+        for (int k = 0; k < count; k++) out[k] = HFr::load(mine + 4 * k);
+        return 0;
+    }
+    std::vector<uint64_t> send(mine, mine + 4 * (size_t)count), all((size_t)world * 4 * count);
+    if (pk->shard.allgather(pk->shard.user, send.data(), all.data(), (size_t)count * 32) != 0)
+        return pb_fail(ctx, PB200_ERR_ARG, "sharded evaluation", "the all-gather callback failed", __FILE__, __LINE__);
+    for (int k = 0; k < count; k++) {
+        HFr acc = HFr::zero();
+        for (uint32_t r = 0; r < world; r++) acc = acc + HFr::load(&all[((size_t)r * count + k) * 4]);
+        out[k] = acc;
+    }
+    return 0;
 }
 
 struct RoundClock {
@@ -994,9 +1018,10 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
     {
         EvalArgs A;
         int j = 0;
-        auto job = [&](const Fr *p, size_t len, int point) {
+        auto job = [&](const Fr *p, size_t len, int point) {   // sharded: this rank's coefficient slice of every polynomial
             A.p[j] = p;
-            A.len[j] = p ? (uint32_t)len : 0;
+            A.len[j] = p ? (uint32_t)(len / world) : 0;
+            A.off[j] = p ? (uint32_t)(pk->shard.rank * (len / world)) : 0;
             A.point[j] = point;
             j++;
         };
@@ -1014,14 +1039,14 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
         A.points[0] = to_dev(z);
         A.points[1] = to_dev(zw);
         A.partial = partial;
-        A.tiles = cdiv(N4, kEvalTile);
+        A.tiles = cdiv(N4 / world, kEvalTile);
         poly_eval_partial_kernel<<<dim3(A.tiles, j), 256, 0, st>>>(A);
         PB_LAUNCHED(ctx);
         poly_eval_final_kernel<<<j, 256, 0, st>>>(partial, A.tiles, scal + 8);
         PB_LAUNCHED(ctx);
         PB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, scal + 8, E_COUNT * sizeof(Fr), cudaMemcpyDeviceToHost, st));
         PB_CUDA(ctx, cudaStreamSynchronize(st));
-        for (int k = 0; k < E_COUNT; k++) ev[k] = HFr::load((const uint64_t *)ctx->pinned + 4 * k);
+        PB_TRY(sum_over_ranks(ctx, pk, (const uint64_t *)ctx->pinned, E_COUNT, ev));
     }
     const HFr one = HFr::one();
     const HFr zn = z.pow_u64(n);
@@ -1080,19 +1105,20 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
     {
         EvalArgs A;
         A.p[0] = pk->lin_poly;
-        A.len[0] = n32;
+        A.len[0] = n32 / world;
+        A.off[0] = pk->shard.rank * (n32 / world);
         A.point[0] = 0;
         A.points[0] = to_dev(z);
         A.points[1] = to_dev(zw);
         A.partial = partial;
-        A.tiles = cdiv(n, kEvalTile);
+        A.tiles = cdiv(n / world, kEvalTile);
         poly_eval_partial_kernel<<<dim3(A.tiles, 1), 256, 0, st>>>(A);
         PB_LAUNCHED(ctx);
         poly_eval_final_kernel<<<1, 256, 0, st>>>(partial, A.tiles, scal + 8);
         PB_LAUNCHED(ctx);
         PB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, scal + 8, sizeof(Fr), cudaMemcpyDeviceToHost, st));
         PB_CUDA(ctx, cudaStreamSynchronize(st));
-        ev[E_COUNT] = HFr::load((const uint64_t *)ctx->pinned);  // r(z)
+        PB_TRY(sum_over_ranks(ctx, pk, (const uint64_t *)ctx->pinned, 1, &ev[E_COUNT]));  // r(z)
     }
     {
         const struct { const char *label; int idx; } order[17] = {

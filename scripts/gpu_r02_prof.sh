@@ -18,5 +18,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-fi
 echo "ncu launches rc=$?"
 ncu -i gpurun_out/prof_r02.ncu-rep --page raw --csv > gpurun_out/prof_r02_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_prove_r02.ncu-rep --page raw --csv > gpurun_out/prof_prove_r02_raw.csv 2>/dev/null
-timeout 600 python scripts/msm_tail_scaling.py > gpurun_out/r02_msm_tail_scaling.json 2> gpurun_out/r02_msm_tail_scaling.err; cat gpurun_out/r02_msm_tail_scaling.json
+# per-instruction stall samples of the NTT passes (source page), compressed; the 50 MB reports themselves stay on the box
+ncu -i gpurun_out/prof_r02.ncu-rep --page source --csv -k regex:ntt_pass_tma_kernel 2>/dev/null | gzip -9 > gpurun_out/prof_r02_ntt_source.csv.gz
+rm -f gpurun_out/*.ncu-rep
 ls -la gpurun_out | grep r02
