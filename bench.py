@@ -300,15 +300,15 @@ def timed_proves(setup, args, torch, stream, dist=None, device=None):
     e1.record(stream)
     barrier()
     wall_dev_ms = 1e3 * (time.perf_counter() - t0) / args.steps
-    if args.steps * wall_dev_ms < 400.0:    # keep the sampler over a few more (untimed) steps so that it sees the GPU under load
-        for _ in range(int(400.0 / max(wall_dev_ms, 1.0)) + 1):
-            setup.prove_dev()
-    clocks = sampler.stop()
     launches = ctx.launch_count() - l0
     dev_ms = e0.elapsed_time(e1) / args.steps
     sums = {k: ctx.profile_sum_ms(k) for k in ("msm.accumulate", "msm.sort", "msm.partials", "msm.reduce", "msm.total", "ntt.total")}
     rounds = {"round%d" % k: ctx.profile_sum_ms("prove.round%d" % k)[0] / args.steps for k in range(1, 6)}
     ctx.profile_enable(False)
+    if args.steps * wall_dev_ms < 400.0:    # keep the sampler over a few more (untimed) steps so that it sees the GPU under load
+        for _ in range(int(400.0 / max(wall_dev_ms, 1.0)) + 1):
+            setup.prove_dev()
+    clocks = sampler.stop()
     for _ in range(min(args.warmup, 2)):
         proofs.add(setup.prove_host())
     barrier()
