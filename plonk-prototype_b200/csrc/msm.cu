@@ -269,10 +269,23 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     cfg.L2 = 16;
     const uint32_t n_win = pre_stride ? batch : cfg.W;   // bucket sets (windows to reduce / combine)
     const uint32_t TB = n_win << cfg.nb_log;          // total buckets
-    {   // chunk size for the bucket reduction: aim for ≥ 64 Ki chunk threads, 8 ≤ K ≤ 256
-        uint32_t k_log = 3;
-        while (k_log < 8 && (TB >> (k_log + 1)) >= 65536) k_log++;
-        cfg.K_log = std::min(k_log, cfg.nb_log);
+    {   // Chunk size K of the bucket reduction (one thread per K consecutive buckets: 2K running-sum additions plus one small
+        // scalar multiple of ≈ 22 addition-equivalents for the chunk's offset).  The kernel runs 2 CTAs of 128 threads per SM
+        // (255 registers), every thread does the same work, so the time is (number of waves) × (work per thread): choose the K
+        // that minimises it — larger K amortises the scalar multiple, smaller K fills the machine, and a partly filled last
+        // wave costs a whole one.  (Measured, profiles/msm_tail_scaling_r02.json: the old fixed rule — ≥ 64 Ki threads — ran
+        // 2^19 buckets as 2 waves of K = 8 where one wave of K = 16 does the same work in 2/3 of the time.)
+        const uint32_t slots = (uint32_t)ctx->sm_count * 2;
+        double best = 1e300;
+        uint32_t best_k = 3;
+        for (uint32_t k_log = 2; k_log <= 8 && k_log <= cfg.nb_log; k_log++) {
+            const uint64_t ctas = (((uint64_t)TB >> k_log) + 127) / 128;
+            const uint64_t waves = (ctas + slots - 1) / slots;
+            const double cost = (double)waves * (2.0 * (double)(1u << k_log) + 22.0);
+            if (cost < best) { best = cost; best_k = k_log; }
+        }
+        if (const char *v = getenv("PB200_MSM_REDUCE_K_LOG")) best_k = std::min<uint32_t>((uint32_t)atoi(v), cfg.nb_log);  // tests / tuning
+        cfg.K_log = best_k;
     }
     const uint32_t n_chunks = TB >> cfg.K_log, chunks_per_window = n_chunks / n_win;
 

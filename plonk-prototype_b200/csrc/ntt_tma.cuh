@@ -8,7 +8,7 @@
 //     by cp.async.bulk.tensor.2d stores (UTMASTG): no LDG/STG and no address arithmetic in the instruction stream;
 //   * every butterfly round reads / writes a scalar as two LDS.128 / STS.128 (the planar layout of the first kernel
 //     needed eight 32-bit accesses); with the swizzle a quarter-warp's eight 16-byte accesses fall into eight different
-//     bank groups in the load loop, the store rounds and every round with b_lo ≥ 1 (the last round is 2-way);
+//     bank groups in the staging loop, every round with b_lo ≥ 1 and the final write-back (only the last round's load is 2-way);
 //   * the butterfly twiddles of all rounds are staged into shared memory by one cp.async.bulk (UBLKCP) from a compact
 //     per-round image built with the plan, so the rounds issue no global loads at all;
 //   * the bit reversal and the inter-pass twiddle / coset factor are applied in registers after the last round, the
@@ -182,6 +182,21 @@ ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
             tma::sts_fr(tile + tma::tile_off(x, cc), g_load(src + (((uint64_t)row << S) + x)));
         }
     }
+    // The last round's thread ↔ row assignment is bit-reversed (rows (brev(tx) << 3) | e), so that the output rows k a
+    // quarter-warp writes differ in their LOW bits and the write-back to the tile is bank-conflict free (ncu, first version:
+    // 25 % of the shared wavefronts were conflicts, half of them from that store).  k = brev_S(x) = (brev3(e) << (S−3)) | tx.
+    const uint32_t tx_rev = __brev(tx) >> (32 - (S - 3));
+    if (p.store_mode) {
+        // the inter-pass twiddles / coset factors this thread multiplies by at the very end come from a table as long as the
+        // vector (DRAM): start pulling them towards L2 now, the butterflies hide the latency
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const uint32_t e_rev = ((e & 1) << 2) | (e & 2) | ((e >> 2) & 1);
+            const uint32_t k = (e_rev << (S - 3)) | tx;
+            const uint64_t idx = p.store_mode == 4 ? (((uint64_t)k << p.ncol_log) + col0 + c) : ((uint64_t)(rowrev0 + c) + ((uint64_t)k << p.nrows_log));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.s_full + idx));
+        }
+    }
     tma::mbar_wait(bar, 0);
     __syncthreads();
     if (p.load_mode == 2) {   // coset_fft: a_j ← a_j·7^j on the way in (one multiplier instance, its own sweep over the tile)
@@ -226,7 +241,7 @@ ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     }
     // last round on bits [0, 2]: twiddles are ω₈^k
 #pragma unroll
-    for (int e = 0; e < 8; e++) a[e] = tma::lds_fr(tile + tma::tile_off((tx << 3) | (uint32_t)e, c));
+    for (int e = 0; e < 8; e++) a[e] = tma::lds_fr(tile + tma::tile_off((tx_rev << 3) | (uint32_t)e, c));
     __syncthreads();   // every thread has read its rows: they may now be overwritten with outputs of other rows
     if (b_top >= 2) {
         bfly1(a[0], a[4]);
@@ -244,7 +259,7 @@ ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     for (int e = 0; e < 8; e += 2) bfly1(a[e], a[e + 1]);
     // bit reversal + inter-pass twiddle / coset factor in registers, then to the tile at the OUTPUT row k
     {
-        const uint32_t k_hi = __brev(tx) >> (32 - (S - 3));   // k = brev_S((tx << 3) | e) = (brev3(e) << (S−3)) | brev_{S−3}(tx)
+        const uint32_t k_hi = tx;   // k = brev_S((tx_rev << 3) | e) = (brev3(e) << (S−3)) | brev_{S−3}(tx_rev) = … | tx
 #pragma unroll
         for (int e = 0; e < 8; e++) {
             const uint32_t e_rev = ((e & 1) << 2) | (e & 2) | ((e >> 2) & 1);

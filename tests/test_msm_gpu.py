@@ -284,3 +284,25 @@ def test_batched_msm_matches_single_calls(ctx, oracle, n, batch, pre):
     finally:
         ctx.free(dev)
         ctx.srs_free(srs)
+
+
+@pytest.mark.parametrize("k_log", [2, 3, 5, 8])
+def test_bucket_reduction_chunk_sizes(ctx, oracle, monkeypatch, k_log):
+    """The bucket reduction's chunk size is chosen by a wave / work cost model; every choice must give the same group
+    element (plain and pre-doubled SRS, skewed digits included)."""
+    monkeypatch.setenv("PB200_MSM_REDUCE_K_LOG", str(k_log))
+    n = 1 << 14
+    pts = oracle.synthetic_bases(n)
+    srs = ctx.srs_upload(pts)
+    srs_pre = ctx.srs_upload(pts)
+    ctx.srs_precompute(srs_pre)
+    rnd = model.random_fr(0x4B + k_log, n)
+    try:
+        for name, vals in (("random", rnd), ("eight_bit", [v & 0xFF for v in rnd]), ("all_r_minus_1", [model.R - 1] * n)):
+            s = oracle.fr_to_mont(oracle.ints_to_limbs(vals, 4))
+            want = model.g1_mul(model.G1_GEN, closed_form_msm_scalar(s, A, D, model.R, model.FR_MONT_R))
+            assert aff(oracle, ctx.msm(srs, s)) == want, (name, "plain")
+            assert aff(oracle, ctx.msm(srs_pre, s)) == want, (name, "pre")
+    finally:
+        ctx.srs_free(srs)
+        ctx.srs_free(srs_pre)

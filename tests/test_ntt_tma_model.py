@@ -131,7 +131,8 @@ def run_pass(src, dst, L, p, img):
         regs = {}
         for tid in range(NTHR):                                       # every thread reads its rows, then the barrier
             c, tx = tid & 3, tid >> 2
-            regs[tid] = [tile.lds_fr(tile_off((tx << 3) | e, c)) for e in range(8)]
+            tx_rev = brev(tx, S - 3)                                   # bit-reversed row assignment of the last round
+            regs[tid] = [tile.lds_fr(tile_off((tx_rev << 3) | e, c)) for e in range(8)]
         for tid in range(NTHR):
             c, tx = tid & 3, tid >> 2
             a = regs[tid]
@@ -147,7 +148,7 @@ def run_pass(src, dst, L, p, img):
                 bfly(a, 5, 7, w4)
             for e in range(0, 8, 2):
                 bfly(a, e, e + 1, 1)
-            k_hi = brev(tx, S - 3)
+            k_hi = tx
             for e in range(8):
                 e_rev = ((e & 1) << 2) | (e & 2) | ((e >> 2) & 1)
                 k = (e_rev << (S - 3)) | k_hi
@@ -265,5 +266,9 @@ def test_swizzle_is_conflict_free_where_claimed():
             assert len({(tile_off(x, 1) >> 4) & 7 for x in range(q, q + 8)}) == 8
         for q in range(0, 64, 8):                                         # coset sweep / stores: lanes = consecutive (x, c)
             assert len({(tile_off(i >> 2, i & 3) >> 4) & 7 for i in range(q, q + 8)}) == 8
-        groups = {(tile_off((tx << 3) | 5, c) >> 4) & 7 for tx in (0, 1) for c in range(4)}
-        assert len(groups) == 4                                            # last round: 2-way
+        groups = {(tile_off((brev(tx, S - 3) << 3) | 5, c) >> 4) & 7 for tx in (0, 1) for c in range(4)}
+        assert len(groups) == 4                                            # last round's load: 2-way
+        for q in range(0, 1 << (S - 1), 8):                                # … its write-back to the output rows: conflict free
+            for e in range(8):
+                e_rev = ((e & 1) << 2) | (e & 2) | ((e >> 2) & 1)
+                assert len({(tile_off((e_rev << (S - 3)) | (tid >> 2), tid & 3) >> 4) & 7 for tid in range(q, q + 8)}) == 8
