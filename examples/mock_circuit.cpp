@@ -82,6 +82,23 @@ int main() {
         tampered[600] ^= 1;
         CHECK(!verify_proof(prover.verifier_key(), prover.padded_size(), label, tampered, cs.public_inputs_sparse_store(), tau));
 
+        // MockCircuit::prove_ownership (/root/reference/src/zk/circuits.rs:63-66): sk·G computed in circuit by the fixed-base
+        // widget equals the public key, which enters as two public inputs
+        {
+            Prover own = Prover::new_(ctx, "manta-prove-ownership");
+            StandardComposer &c2 = own.mut_cs();
+            const BlsScalar sk = BlsScalar::from(0x0A11CE5EC2E7ull);
+            const jubjub::Affine pk_point = jubjub::mul(jubjub::generator(), sk.reduce());
+            const Point circuit_pk = c2.fixed_base_scalar_mul(c2.add_input(sk), jubjub::generator());
+            c2.assert_equal_public_point(circuit_pk, pk_point);
+            own.preprocess(ck);
+            const ProofBytes p2 = own.prove(ck);
+            CHECK(verify_proof(own.verifier_key(), own.padded_size(), "manta-prove-ownership", p2, c2.public_inputs_sparse_store(), tau));
+            std::map<uint32_t, BlsScalar> other_key = c2.public_inputs_sparse_store();
+            other_key.begin()->second = other_key.begin()->second + BlsScalar::one();
+            CHECK(!verify_proof(own.verifier_key(), own.padded_size(), "manta-prove-ownership", p2, other_key, tau));
+        }
+
         // EvaluationDomain round trips and the error rule
         EvaluationDomain dom = EvaluationDomain::new_(ctx, 1000);
         CHECK(dom.size() == 1024);

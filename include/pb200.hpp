@@ -41,6 +41,12 @@ struct BlsScalar {
     static BlsScalar one() { return BlsScalar(hostf::HFr::one()); }
     static BlsScalar from(uint64_t x) { return BlsScalar(hostf::HFr::from_u64(x)); }
     static BlsScalar pow_of_2(uint64_t k) { return from(2).pow(k); }
+    // `from_raw([u64; 4])`: canonical little-endian limbs → Montgomery form
+    static BlsScalar from_raw(uint64_t l0, uint64_t l1, uint64_t l2, uint64_t l3) {
+        hostf::HFr r = hostf::HFr::zero();
+        r.l[0] = l0; r.l[1] = l1; r.l[2] = l2; r.l[3] = l3;
+        return BlsScalar(r * hostf::HFr::r2());
+    }
     BlsScalar operator+(const BlsScalar &o) const { return BlsScalar(v + o.v); }
     BlsScalar operator-(const BlsScalar &o) const { return BlsScalar(v - o.v); }
     BlsScalar operator*(const BlsScalar &o) const { return BlsScalar(v * o.v); }
@@ -189,6 +195,59 @@ inline G1Projective msm_variable_base(Context &ctx, const std::vector<G1Affine> 
 // ---- StandardComposer ------------------------------------------------------------------------------------------
 typedef uint32_t Variable;
 
+// ---- JubJub on the host (dusk-jubjub 0.10, /root/reference/Cargo.toml:21): witness generation for the ECC gadgets ------
+// −x² + y² = 1 + d·x²·y², d = −10240/10241; GENERATOR has y = 18 (x = the root of the curve equation in the prime-order
+// subgroup), GENERATOR_NUMS as published — see plonk-prototype_b200/jubjub.py and tests/test_widgets_cpu.py.
+namespace jubjub {
+struct Affine {
+    BlsScalar x, y;
+};
+inline BlsScalar edwards_d() { return -(BlsScalar::from(10240) * BlsScalar::from(10241).invert().second); }
+inline Affine identity() { return {BlsScalar::zero(), BlsScalar::one()}; }
+inline Affine generator() {
+    return {BlsScalar::from_raw(0x4df7b7ffec7beacaull, 0x2e3ebb21fd6c54edull, 0xf1fbf02d0fd6cce6ull, 0x3fd2814c43ac65a6ull), BlsScalar::from(18)};
+}
+inline Affine generator_nums() {
+    return {BlsScalar::from_raw(0x921710179df76377ull, 0x931e316a39fe4541ull, 0xbd9514c773fd4456ull, 0x5e67b8f316f414f7ull),
+            BlsScalar::from_raw(0x6705b707162e3ef8ull, 0x9949ba0f82a5507aull, 0x7b162dbeeb3b34fdull, 0x43d80eb3b2f3eb1bull)};
+}
+inline Affine add(const Affine &p, const Affine &q) {
+    const BlsScalar t = edwards_d() * p.x * q.x * p.y * q.y, one = BlsScalar::one();
+    return {(p.x * q.y + p.y * q.x) * (one + t).invert().second, (p.y * q.y + p.x * q.x) * (one - t).invert().second};
+}
+inline Affine neg(const Affine &p) { return {-p.x, p.y}; }
+inline Affine mul(Affine p, std::array<uint64_t, 4> k) {
+    Affine acc = identity();
+    for (int i = 0; i < 256; i++) {
+        if ((k[i >> 6] >> (i & 63)) & 1) acc = add(acc, p);
+        p = add(p, p);
+    }
+    return acc;
+}
+// `Fr::compute_windowed_naf(2)`: 256 digits in {−1, 0, 1}, least significant first
+inline std::array<int8_t, 256> wnaf2(std::array<uint64_t, 4> k) {
+    std::array<int8_t, 256> out{};
+    auto is_zero = [&]() { return (k[0] | k[1] | k[2] | k[3]) == 0; };
+    for (int i = 0; i < 256 && !is_zero(); i++) {
+        if (k[0] & 1) {
+            const int d = 2 - (int)(k[0] & 3);   // k mod 4 = 1 → +1, = 3 → −1
+            out[i] = (int8_t)d;
+            if (d == 1) {
+                k[0] -= 1;   // k is odd: no borrow
+            } else {
+                for (int l = 0; l < 4 && ++k[l] == 0; l++) {}
+            }
+        }
+        for (int l = 0; l < 4; l++) k[l] = (k[l] >> 1) | (l < 3 ? k[l + 1] << 63 : 0);
+    }
+    return out;
+}
+}  // namespace jubjub
+
+struct Point {  // constraint_system::ecc::Point: a pair of variables
+    Variable x, y;
+};
+
 class StandardComposer {
   public:
     StandardComposer() {
@@ -238,13 +297,76 @@ class StandardComposer {
         constrain_to_constant(v, value, nullptr);
         return v;
     }
+    void assert_equal(Variable a, Variable b) {
+        row(a, b, zero_var_, zero_var_, BlsScalar::zero(), BlsScalar::one(), -BlsScalar::one(), BlsScalar::zero(), BlsScalar::zero(), nullptr);
+    }
+    // ---- constraint_system::ecc (call sites /root/reference/src/zk/gadgets.rs:34-40, circuits.rs:64-65) ----------------
+    // 256 rows of the fixed-base widget over the 2-bit windowed NAF of the scalar (most significant digit first) plus one
+    // plain row with the final accumulators; throws if the scalar is not a canonical JubJub scalar (upstream unwraps).
+    Point fixed_base_scalar_mul(Variable jubjub_scalar, const jubjub::Affine &generator) {
+        const int num_bits = 256;
+        std::vector<jubjub::Affine> multiples(num_bits);
+        multiples[num_bits - 1] = generator;   // multiples[i] = 2^(255−i)·G pairs with the i-th digit from the top
+        for (int i = num_bits - 2; i >= 0; i--) multiples[i] = jubjub::add(multiples[i + 1], multiples[i + 1]);
+        const std::array<uint64_t, 4> k = variables_[jubjub_scalar].reduce();
+        static const uint64_t order[4] = {0xd0970e5ed6f72cb7ull, 0xa6682093ccc81082ull, 0x06673b0101343b00ull, 0x0e7db4ea6533afa9ull};
+        bool below = false;
+        for (int l = 3; l >= 0; l--) {
+            if (k[l] != order[l]) { below = k[l] < order[l]; break; }
+        }
+        if (!below) throw Error("fixed_base_scalar_mul: the scalar is not a canonical JubJub scalar");
+        const std::array<int8_t, 256> naf = jubjub::wnaf2(k);
+        std::vector<BlsScalar> scalar_acc{BlsScalar::zero()}, xy_alphas;
+        std::vector<jubjub::Affine> point_acc{jubjub::identity()};
+        for (int i = 0; i < num_bits; i++) {
+            const int entry = naf[num_bits - 1 - i];
+            const jubjub::Affine to_add = entry == 0 ? jubjub::identity() : (entry == 1 ? multiples[i] : jubjub::neg(multiples[i]));
+            BlsScalar acc = scalar_acc[i] + scalar_acc[i];
+            if (entry == 1) acc = acc + BlsScalar::one();
+            if (entry == -1) acc = acc - BlsScalar::one();
+            scalar_acc.push_back(acc);
+            point_acc.push_back(jubjub::add(point_acc[i], to_add));
+            xy_alphas.push_back(to_add.x * to_add.y);
+        }
+        for (int i = 0; i < num_bits; i++) {
+            const Variable acc_x = add_input(point_acc[i].x), acc_y = add_input(point_acc[i].y), accumulated_bit = add_input(scalar_acc[i]);
+            if (i == 0) {
+                constrain_to_constant(acc_x, BlsScalar::zero());
+                constrain_to_constant(acc_y, BlsScalar::one());
+                constrain_to_constant(accumulated_bit, BlsScalar::zero());
+            }
+            const Variable xy_alpha = add_input(xy_alphas[i]);
+            row(acc_x, acc_y, xy_alpha, accumulated_bit, BlsScalar::zero(), multiples[i].x, multiples[i].y, BlsScalar::zero(),
+                multiples[i].x * multiples[i].y, nullptr, BlsScalar::zero(), /*q_arith=*/false, Q_FIXED);
+        }
+        const Variable acc_x = add_input(point_acc[num_bits].x), acc_y = add_input(point_acc[num_bits].y);
+        const Variable last_accumulated_bit = add_input(scalar_acc[num_bits]);
+        row(acc_x, acc_y, zero_var_, last_accumulated_bit, BlsScalar::zero(), BlsScalar::zero(), BlsScalar::zero(), BlsScalar::zero(),
+            BlsScalar::zero(), nullptr);   // big_add_gate with zero selectors: the "next" row of the last widget row
+        assert_equal(last_accumulated_bit, jubjub_scalar);
+        return {acc_x, acc_y};
+    }
+    Point point_addition_gate(const Point &a, const Point &b) {
+        const jubjub::Affine s = jubjub::add({variables_[a.x], variables_[a.y]}, {variables_[b.x], variables_[b.y]});
+        const Variable x1_y2 = add_input(variables_[a.x] * variables_[b.y]);
+        const Variable x3 = add_input(s.x), y3 = add_input(s.y);
+        const BlsScalar z = BlsScalar::zero();
+        row(a.x, a.y, b.x, b.y, z, z, z, z, z, nullptr, z, /*q_arith=*/false, Q_VAR);
+        row(x3, y3, zero_var_, x1_y2, z, z, z, z, z, nullptr, z, /*q_arith=*/false);
+        return {x3, y3};
+    }
+    void assert_equal_public_point(const Point &p, const jubjub::Affine &public_point) {
+        const BlsScalar nx = -public_point.x, ny = -public_point.y;
+        constrain_to_constant(p.x, BlsScalar::zero(), &nx);
+        constrain_to_constant(p.y, BlsScalar::zero(), &ny);
+    }
 
     // column images for pb200_preprocess / pb200_prove
     pb200_circuit circuit() const {
         pb200_circuit c;
         c.n_gates = circuit_size();
         c.n_vars = variables_.size();
-        for (int k = 0; k < 11; k++) c.selectors[k] = k < 7 ? reinterpret_cast<const uint64_t *>(q_[k].data()) : nullptr;
+        for (int k = 0; k < 11; k++) c.selectors[k] = (k < 7 || used_[k]) ? reinterpret_cast<const uint64_t *>(q_[k].data()) : nullptr;
         for (int k = 0; k < 4; k++) c.wires[k] = w_[k].data();
         return c;
     }
@@ -252,11 +374,15 @@ class StandardComposer {
     const std::map<uint32_t, BlsScalar> &public_inputs_sparse_store() const { return pi_; }
 
   private:
-    enum { QM, QL, QR, QO, QC, Q4, QARITH };
+    enum { QM, QL, QR, QO, QC, Q4, QARITH, Q_RANGE, Q_LOGIC, Q_FIXED, Q_VAR };
+    // one row of all eleven selector columns; `widget` = Q_FIXED / Q_VAR sets that selector to one
     void row(Variable a, Variable b, Variable c, Variable d, const BlsScalar &q_m, const BlsScalar &q_l, const BlsScalar &q_r,
-             const BlsScalar &q_o, const BlsScalar &q_c, const BlsScalar *pi, const BlsScalar &q_4 = BlsScalar::zero()) {
-        const BlsScalar vals[7] = {q_m, q_l, q_r, q_o, q_c, q_4, BlsScalar::one()};
+             const BlsScalar &q_o, const BlsScalar &q_c, const BlsScalar *pi, const BlsScalar &q_4 = BlsScalar::zero(), bool q_arith = true,
+             int widget = -1) {
+        const BlsScalar vals[7] = {q_m, q_l, q_r, q_o, q_c, q_4, q_arith ? BlsScalar::one() : BlsScalar::zero()};
         for (int k = 0; k < 7; k++) q_[k].push_back(vals[k]);
+        for (int k = 7; k < 11; k++) q_[k].push_back(k == widget ? BlsScalar::one() : BlsScalar::zero());
+        if (widget >= 0) used_[widget] = true;
         const Variable w[4] = {a, b, c, d};
         for (int k = 0; k < 4; k++) w_[k].push_back(w[k]);
         if (pi) pi_[(uint32_t)(w_[0].size() - 1)] = *pi;
@@ -268,7 +394,8 @@ class StandardComposer {
             BlsScalar::one());
         row(m20, six, seven, zero_var_, BlsScalar::one(), BlsScalar::one(), BlsScalar::one(), BlsScalar::one(), BlsScalar::from(127), nullptr);
     }
-    std::vector<BlsScalar> q_[7];
+    std::vector<BlsScalar> q_[11];
+    bool used_[11] = {};
     std::vector<Variable> w_[4];
     std::vector<BlsScalar> variables_;
     std::map<uint32_t, BlsScalar> pi_;
