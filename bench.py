@@ -335,7 +335,11 @@ def prove_roofline(setup, timed, args, imad_peak, n_per_msm):
     return {
         "bound": "imad", "kernel": "msm_accumulate_kernel", "achieved": alg / (acc_per_step * 1e-3) / 1e12, "peak": imad_peak / 1e12,
         "unit": "T IMAD.WIDE.U32 lane-op/s", "frac": alg / (acc_per_step * 1e-3) / imad_peak,
-        "traffic": None, "kernel_ms_per_step": acc_per_step, "launches_per_step": acc_launches / args.steps,
+        # dram__bytes_read.sum + dram__bytes_write.sum per accumulate launch inside a 2^20-gate prove on one GPU, ncu --set full
+        # (profiles/ncu_prove_r02_summary.txt: 11.1 GB for a batch-of-4 launch, 2.87 GB for a single one; 4 launches = 11 MSMs per
+        # proof ⇒ ≈ 7.7 GB per launch on average, against ≈ 3.9 GB algorithmic — 8-byte entries + 96-byte base gathers)
+        "traffic": 7.7e9 if (n_per_msm == 1 << 20) else None,
+        "kernel_ms_per_step": acc_per_step, "launches_per_step": acc_launches / args.steps,
         "avg_launch_ms": acc_ms / max(acc_launches, 1), "share_of_step": acc_per_step / timed["dev_ms"],
         "peak_source": "pb200_imad_peak: IMAD.WIDE.U32.X carry-chain microbenchmark run in this process (MEASURED_PEAKS.json holds no integer peak)",
         "model": "per proof 11 MSMs x N*ceil(256/(log2N-4))*10 Fp mul*300 IMAD.WIDE with N = %d (SURVEY.md §8d, unchanged; the kernel runs wider "

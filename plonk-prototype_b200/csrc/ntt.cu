@@ -523,10 +523,10 @@ static size_t ntt_tma_smem_bytes(uint32_t S) {
 }
 // One pass over `nb` vectors of 2^L scalars (src / dst point at the first of them).
 static int ntt_launch_tma(pb200_ctx *ctx, const NttPassTma &tp, const Fr *src, Fr *dst, uint32_t L, uint32_t blocks, uint32_t nb) {
-    // measured on B200 (profiles/ntt_sweep_r02.json): up to S = 8 three CTAs of ≤ 168 registers beat four of 128 (2^24: 3.48 vs
-    // 3.69 ms); at S = 9 (256 threads per CTA) the wide variant leaves one CTA per SM and loses (2^26: 18.3 vs 15.1 ms)
+    // measured on B200 (profiles/ntt_sweep_r02.json): 512 threads per SM at 128 registers and 384 at ≤ 168 tie up to S = 8
+    // (2^24: 3.40 ms both) and the wide variant loses at S = 9, where it leaves one CTA per SM (2^26: 17.1 vs 14.4 ms)
     static const char *regs_env = getenv("PB200_NTT_TMA_REGS");
-    const bool wide_regs = regs_env ? !strcmp(regs_env, "168") : tp.S <= 8;
+    const bool wide_regs = regs_env != nullptr && !strcmp(regs_env, "168");
     const uint32_t box_rows = std::min(1u << tp.S, 256u);
     CUtensorMap map_in, map_out;
     if (tp.type == 0) {

@@ -332,11 +332,13 @@ __global__ void __launch_bounds__(256) lincomb_kernel(const LcArgs A) {
         if (j < A.len[k]) acc = acc + A.c[k] * ld_fr(A.p[k] + j);
     st_fr(A.out + j, acc);
 }
-// Polynomial::evaluate for many (polynomial, point) pairs at once.  A CTA covers 2048 coefficients: each thread
-// runs Horner over 8 of them, scales by point^(first index), and the CTA tree-sums into one partial; a second
+// Polynomial::evaluate for many (polynomial, point) pairs at once.  A CTA covers 8192 coefficients: each thread
+// runs Horner over 32 of them, scales by point^(first index), and the CTA tree-sums into one partial; a second
 // launch adds the partials of each job.
 constexpr int kMaxJobs = 20;
-constexpr uint32_t kEvalPerThread = 8, kEvalTile = 256 * kEvalPerThread;
+// (32 coefficients per thread: the x^first factor costs ≈ 30 multiplications per thread, so 8 per thread spent 4/5 of the
+// kernel on it — 1.3 ms per proof at 2^20 gates)
+constexpr uint32_t kEvalPerThread = 32, kEvalTile = 256 * kEvalPerThread;
 struct EvalArgs {
     const Fr *p[kMaxJobs];
     uint32_t len[kMaxJobs];    // coefficients this launch covers: [off, off + len)

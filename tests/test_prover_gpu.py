@@ -285,14 +285,21 @@ def test_cxx_host_layer_example_runs(ctx):
     assert "proof verified" in r.stdout
 
 
-def test_unsupported_widget_is_rejected_loudly(ctx):
+def test_every_selector_column_is_accepted_and_an_unsatisfied_widget_row_fails_verification(ctx):
+    """Round 1 rejected q_logic / q_fixed_group_add / q_variable_group_add; all eleven columns are widgets now.  Switching the
+    logic widget on over rows it does not hold for must still prove (the prover does not check satisfiability) but not verify."""
     import plonk_prototype_b200 as pb
     comp = pm.synthetic_circuit(13)
     sel, wires = columns(comp)
     sel[pm.SELECTORS.index("q_logic")] = mont([1] * comp.n)
-    pp = pb.PublicParameters(15, 5, ctx)
-    with pytest.raises(pb.Pb200Error):
-        ctx.preprocess(pp.srs, sel, wires, len(comp.values), b"x")
+    tau = 5
+    pp = pb.PublicParameters(15, tau, ctx)
+    pk, vk = ctx.preprocess(pp.srs, sel, wires, len(comp.values), b"x")
+    pis = sorted(comp.pi.items())
+    pos, piv = np.asarray([p for p, _ in pis], dtype=np.uint32), mont([v for _, v in pis])
+    proof = ctx.prove(pp.srs, pk, mont(comp.values), pos, piv)
+    assert not pb.verify(vk, 16, b"x", proof, pos, piv, pb.opening_key_from_tau(mont([tau])))
+    ctx.prover_key_free(pk)
     pp.close()
 
 
