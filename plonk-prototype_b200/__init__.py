@@ -5,4 +5,4 @@ from .domain import EvaluationDomain, InvalidEvalDomainSize, default_context  # 
 from .msm import msm_variable_base, CommitKey, g1_to_bytes  # noqa: F401
 from .dist_ntt import DistributedDomain, ShardSpec, GpuBackend, PeerBuffers  # noqa: F401
 from .prover import StandardComposer, Prover, PublicParameters, ShardedParameters, torch_allgather, torch_device_collectives, scalars_to_mont  # noqa: F401
-from . import gadgets, jubjub  # noqa: F401
+from . import gadgets, jubjub, poseidon  # noqa: F401

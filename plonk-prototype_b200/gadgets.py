@@ -11,9 +11,10 @@ the bound first, and `bits_count` works on the canonical value starting from one
 
 `commitment_gadget` (gadgets.rs:28-41) and `MockCircuit::prove_ownership` (circuits.rs:63-66) go through the composer's
 `fixed_base_scalar_mul` / `point_addition_gate` / `assert_equal_public_point` and the GPU's fixed-base / variable-base
-widgets (csrc/widgets.h).  Not available: `check_hash_inputs` (circuits.rs:69-72) — dusk-poseidon's round constants and
-MDS matrix are generated data of a crate that is not on disk (Cargo.toml:23); it raises NotImplementedError rather than
-build a circuit with made-up constants.
+widgets (csrc/widgets.h).  `check_hash_inputs` (circuits.rs:69-72) uses the Poseidon sponge of
+plonk-prototype_b200/poseidon.py, whose constants are regenerated from the recalled recipe of dusk-hades (the crate is not
+on disk, Cargo.toml:23, and no test vector could be checked): it constrains the function that module's `hash` computes —
+unpinned against the Rust crate.
 """
 from .jubjub import GENERATOR as GENERATOR_EXTENDED, GENERATOR_NUMS as GENERATOR_NUMS_EXTENDED
 from .prover import R
@@ -117,4 +118,8 @@ class MockCircuit:
         composer.assert_equal_public_point(circuit_pk, self.public_key)
 
     def check_hash_inputs(self, composer, public_hash):
-        raise NotImplementedError("dusk-poseidon's sponge gadget (round constants not available offline) is not implemented")
+        """Constrains a public hash to the Poseidon sponge of the private `hash_inputs` (circuits.rs:69-72).  The sponge is
+        plonk-prototype_b200/poseidon.py — constants and padding restated from memory of dusk-poseidon / dusk-hades, unpinned."""
+        from . import poseidon
+        h = poseidon.gadget(composer, self.hash_inputs)
+        composer.constrain_to_constant(h, 0, -public_hash)

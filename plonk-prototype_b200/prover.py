@@ -102,6 +102,14 @@ class StandardComposer:
         """One row of the range widget (q_range = 1): quads c−4d, b−4c, a−4b, d_next−4a ∈ {0,1,2,3}."""
         self._row(a, b, c, d, q_arith=0, q_range=1)
 
+    def big_add(self, q_l_a, q_r_b, q_4_d, q_c, pi=None):
+        """`big_add((q_l, a), (q_r, b), Some((q_4, d)), q_c, pi) -> Variable`: allocates c = q_l·a + q_r·b + q_4·d + q_c + pi."""
+        (q_l, a), (q_r, b) = q_l_a, q_r_b
+        q_4, d = q_4_d if q_4_d is not None else (0, self.zero_var)
+        c = self.add_input(q_l * self.variables[a] + q_r * self.variables[b] + q_4 * self.variables[d] + q_c + (pi or 0))
+        self._row(a, b, c, d, q_l=q_l, q_r=q_r, q_o=-1, q_4=q_4, q_c=q_c, pi=pi)
+        return c
+
     def big_add_gate(self, a, b, c, d, q_l, q_r, q_o, q_4, q_c, pi=None):
         self._row(a, b, c, self.zero_var if d is None else d, q_l=q_l, q_r=q_r, q_o=q_o, q_4=q_4, q_c=q_c, pi=pi)
         return c

@@ -279,8 +279,6 @@ def test_reference_gadget_semantics_on_the_composer_mirror():
     assert cs2.variables[G.range_check(cs2, 100, 1000, w)] == 1
     cs3 = pb.StandardComposer()
     assert cs3.variables[G.range_check(cs3, 100, 1000, G.AllocatedScalar.allocate(cs3, 1000))] == 0   # max is exclusive
-    with pytest.raises(NotImplementedError):
-        G.MockCircuit(None, hash_inputs=[0]).check_hash_inputs(cs3, 0)      # dusk-poseidon's constants are not on disk
 
 
 def test_reference_ecc_gadgets_on_the_composer_mirror():

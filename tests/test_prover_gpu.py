@@ -489,3 +489,20 @@ def test_unsatisfied_ecc_witness_does_not_verify(ctx):
     G.MockCircuit(None, private_key=cs.add_input(0x1111), public_key=jj.mul(jj.GENERATOR, 0x2222)).prove_ownership(cs)
     proof, vk, n, pos, piv, _ = prove_composer(ctx, cs, 0xBAD, b"bad-key")
     assert not pb.verify(vk, n, b"bad-key", proof, pos, piv, pb.opening_key_from_tau(mont([0xBAD])))
+
+
+def test_check_hash_inputs_circuit_proves_and_verifies(ctx, oracle):
+    """MockCircuit::check_hash_inputs (/root/reference/src/zk/circuits.rs:69-72): the Poseidon sponge circuit (2 permutations,
+    2^12 rows) proves on the GPU, verifies against the right public hash only, and matches the C restatement byte for byte."""
+    import plonk_prototype_b200 as pb
+    cs = pb.StandardComposer()
+    inputs = [0xA11CE, 0xB0B, 1 << 250, 42]
+    pb.gadgets.MockCircuit(None, hash_inputs=[cs.add_input(v) for v in inputs]).check_hash_inputs(cs, pb.poseidon.hash(inputs))
+    tau, label = 0x9051D, b"pb200-poseidon"
+    proof, vk, n, pos, piv, (sel, wires, vals, srs_host) = prove_composer(ctx, cs, tau, label)
+    assert n == 4096
+    bh = pb.opening_key_from_tau(mont([tau]))
+    assert pb.verify(vk, n, label, proof, pos, piv, bh)
+    assert not pb.verify(vk, n, label, proof, pos, mont([-(pb.poseidon.hash(inputs) + 1)]), bh)
+    want_proof, want_vk, _, _ = oracle.plonk_prove(sel, wires, vals, pos, piv, srs_host, label, threads=8)
+    assert vk == want_vk and proof == want_proof

@@ -128,3 +128,41 @@ def _srs_fast(oracle, tau, n):
     pts = oracle.srs_setup(oracle.fr_to_mont(oracle.ints_to_limbs([tau], 4))[0], n)
     canon = oracle.fp_from_mont(pts.reshape(-1, 6)).reshape(n, 12)
     return [(oracle.limbs_to_int(r[:6]), oracle.limbs_to_int(r[6:])) for r in canon]
+
+
+def _as_model_composer(cs):
+    """A protocol-model composer holding the rows of a product StandardComposer (for `check()`)."""
+    m = pm.Composer.__new__(pm.Composer)
+    m.q = {k: list(cs.q[k]) for k in pm.SELECTORS}
+    m.w = [list(cs.w_l), list(cs.w_r), list(cs.w_o), list(cs.w_4)]
+    m.values = list(cs.variables)
+    m.pi = {k: v for k, v in cs.public_inputs_sparse_store.items() if v}
+    m.n, m.zero_var = cs.n, cs.zero_var
+    return m
+
+
+def test_poseidon_sponge_gadget_constrains_the_host_hash():
+    """plonk-prototype_b200/poseidon.py (restated from memory of dusk-poseidon / dusk-hades — unpinned): the circuit's output
+    variable carries `hash(messages)`, every row is satisfied, the end-of-message marker separates lengths, and
+    `MockCircuit::check_hash_inputs` (/root/reference/src/zk/circuits.rs:69-72) binds it to a public input."""
+    import plonk_prototype_b200 as pb
+    P = pb.poseidon
+    assert len(P.round_constants()) == 960 and len(set(P.round_constants())) == 960
+    m = P.mds_matrix()
+    assert all(m[i][j] * (i + 5 + j) % R == 1 for i in range(5) for j in range(5))
+    w = P.permutation([1, 2, 3, 4, 5])
+    assert len(w) == 5 and w != [1, 2, 3, 4, 5] and P.permutation([1, 2, 3, 4, 5]) == w
+    assert len({P.hash([7]), P.hash([7, 0]), P.hash([7, 0, 0, 0]), P.hash([7, 0, 0, 0, 0])}) == 4      # padding is injective in the length
+    for msgs in ([3], [3, 1 << 200, 0xDEADBEEF], [1, 2, 3, 4], [R - 1, 5, 6, 7, 8, 9]):
+        cs = pb.StandardComposer()
+        out = P.gadget(cs, [cs.add_input(v) for v in msgs])
+        assert cs.variables[out] == P.hash(msgs)
+        assert _as_model_composer(cs).check()
+    cs = pb.StandardComposer()
+    inputs = [11, 22, 33, 44]
+    circuit = pb.gadgets.MockCircuit(None, hash_inputs=[cs.add_input(v) for v in inputs])
+    circuit.check_hash_inputs(cs, P.hash(inputs))
+    assert _as_model_composer(cs).check() and len(cs.public_inputs_sparse_store) == 1
+    bad = pb.StandardComposer()
+    pb.gadgets.MockCircuit(None, hash_inputs=[bad.add_input(v) for v in inputs]).check_hash_inputs(bad, P.hash(inputs) + 1)
+    assert not _as_model_composer(bad).check()
