@@ -106,6 +106,21 @@ def msm_scalar_slice(log_total, rank, world, out):
     return out
 
 
+def msm_shard_base(rank, n):
+    """Point-range sharding: rank r owns global indices [r·n, (r+1)·n) of the synthetic SRS, i.e. bases
+    (a_r + i·d)·G with a_r = A0 + r·n·D0."""
+    return A0 + rank * n * D0
+
+
+def gather_partials(dist, local_u64x18, world, device):
+    """All-gather of the ranks' 144-byte partial results (as int64) — the only collective on the MSM path."""
+    import torch
+    mine = torch.from_numpy(np.ascontiguousarray(local_u64x18).view(np.int64).copy()).to(device)
+    bufs = [torch.zeros(18, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(bufs, mine)
+    return torch.stack(bufs).cpu().numpy().view(np.uint64)
+
+
 def oracle():
     """The CPU checker (oracle/): cpu_baseline legs, result verification and the reference arm only."""
     p = os.path.join(ROOT, "oracle")
@@ -510,7 +525,7 @@ def bench_msm(ctx, stream, args, torch, imad_peak, dist, rank, world, device):
     import plonk_prototype_b200 as pb
     LT = args.msm_log_n
     n = (1 << LT) // world
-    a_rank = A0 + rank * n * D0
+    a_rank = msm_shard_base(rank, n)
     bases = ctx.malloc(n * 96)
     ctx.synthetic_bases_dev(bases, n, a_rank, D0)
     srs = ctx.srs_wrap_dev(bases, n)
@@ -530,11 +545,9 @@ def bench_msm(ctx, stream, args, torch, imad_peak, dist, rank, world, device):
     def combine(out):
         if dist is None:
             return out
-        mine = torch.from_numpy(np.ascontiguousarray(out).view(np.int64).copy()).to(device)
-        bufs = torch.empty(world * 18, dtype=torch.int64, device=device)
-        dist.all_gather_into_tensor(bufs, mine)  # 144 B per rank over NVLink: the only collective on the MSM path
+        parts = gather_partials(dist, out, world, device)  # 144 B per rank over NVLink: the only collective on the MSM path
         if rank == 0:
-            return ctx.g1_sum(bufs.cpu().numpy().view(np.uint64).reshape(world, 18))
+            return ctx.g1_sum(parts)
         return out
 
     res = combine(ctx.msm_dev(srs, s_dev, n))
