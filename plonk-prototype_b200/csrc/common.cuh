@@ -122,3 +122,9 @@ struct pb200_srs;
 int msm_batch_to_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_dev, size_t n, uint32_t batch,
                      size_t scalar_stride, uint32_t *result_dev, bool *handled);
 int tail_g1_sum_batch(pb200_ctx *ctx, const uint32_t *pts, uint32_t count, uint32_t batch, uint32_t *results);  // msm_tail.cu
+// kzg.cu: a rank's coefficient slice of the Ruffini witness (two phases around a 32-byte all-gather)
+int kzg_witness_slice_phase1(pb200_ctx *ctx, const uint64_t *poly_slice_dev, uint32_t lo, uint32_t cnt, const uint64_t z_mont[4],
+                             uint64_t *q_slice_dev, uint64_t *work_dev, uint64_t slice_total_out[4]);
+int kzg_witness_slice_phase2(pb200_ctx *ctx, uint32_t lo, uint32_t cnt, uint64_t *q_slice_dev, uint64_t *work_dev,
+                             const uint64_t later_slices_total[4]);
+size_t kzg_witness_slice_work_scalars(uint32_t cnt);

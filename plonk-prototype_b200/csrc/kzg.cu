@@ -89,11 +89,12 @@ __global__ void witness_consts_kernel(const Fr *z, Fr *consts) {
     st_fr(consts + 2, Fr::one());
 }
 // b[j] = a[j]·z^j, four consecutive j per thread (one power by square-and-multiply, then running products)
-__global__ void witness_scale_kernel(const Fr *a, Fr *b, uint32_t n, const Fr *consts) {
+// (j_off: global index of a[0] when a / b are a rank's coefficient slice of a sharded polynomial)
+__global__ void witness_scale_kernel(const Fr *a, Fr *b, uint32_t n, const Fr *consts, uint32_t j_off) {
     const uint32_t j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (j0 >= n) return;
     const Fr z = ld_fr(consts + 0);
-    Fr p = z.pow_u32(j0);
+    Fr p = z.pow_u32(j_off + j0);
     for (uint32_t k = 0; k < 4 && j0 + k < n; k++) {
         st_fr(b + j0 + k, ld_fr(a + j0 + k) * p);
         p = p * z;
@@ -146,7 +147,9 @@ __global__ void __launch_bounds__(256) fr_scan_top_kernel(Fr *tile_sums, uint32_
     if (threadIdx.x == 0) st_fr(grand_total, total);
 }
 // q[i] = z^{−(i+1)} · S[i+1]  with S the suffix sums of b (q[n−1] = 0)
-__global__ void __launch_bounds__(256) witness_finish_kernel(const Fr *b, uint32_t n, const Fr *tile_sums, const Fr *consts, Fr *q) {
+// (sliced: indices are global index − j_off, and `carry` = Σ of b over every later slice, gathered from the other ranks)
+__global__ void __launch_bounds__(256) witness_finish_kernel(const Fr *b, uint32_t n, const Fr *tile_sums, const Fr *consts, Fr *q,
+                                                             uint32_t j_off, const Fr *carry) {
     __shared__ uint4 smraw[256 * 2];
     Fr *sm = reinterpret_cast<Fr *>(smraw);
     const uint32_t base = blockIdx.x * kFrScanTile + threadIdx.x * 4;
@@ -157,9 +160,10 @@ __global__ void __launch_bounds__(256) witness_finish_kernel(const Fr *b, uint32
     }
     Fr inc = block_suffix_scan(s, sm, nullptr);
     Fr run = (inc - s) + ld_fr(tile_sums + blockIdx.x);  // Σ of everything after this thread's four elements
+    if (carry) run = run + ld_fr(carry);
     const Fr zinv = ld_fr(consts + 1);
     Fr zi[4];  // z^{−(base+k+1)}
-    zi[0] = zinv.pow_u32(base + 1);
+    zi[0] = zinv.pow_u32(j_off + base + 1);
     for (int k = 1; k < 4; k++) zi[k] = zi[k - 1] * zinv;
     for (int k = 3; k >= 0; k--) {
         // run = S[base+k+1]
@@ -253,13 +257,13 @@ extern "C" int pb200_kzg_witness_dev(pb200_ctx *ctx, const uint64_t *poly_dev, s
         witness_consts_kernel<<<1, 1, 0, st>>>(zd, consts);
         PB_LAUNCHED(ctx);
         // b = a·z^j is staged in the quotient buffer, the finishing pass reads its own tile before overwriting it
-        witness_scale_kernel<<<(n32 + 1023) / 1024, 256, 0, st>>>((const Fr *)poly_dev, q, n32, consts);
+        witness_scale_kernel<<<(n32 + 1023) / 1024, 256, 0, st>>>((const Fr *)poly_dev, q, n32, consts, 0);
         PB_LAUNCHED(ctx);
         fr_scan_tile_sums_kernel<<<n_tiles, 256, 0, st>>>(q, n32, tiles);
         PB_LAUNCHED(ctx);
         fr_scan_top_kernel<<<1, 256, 0, st>>>(tiles, n_tiles, total);
         PB_LAUNCHED(ctx);
-        witness_finish_kernel<<<n_tiles, 256, 0, st>>>(q, n32, tiles, consts, q);
+        witness_finish_kernel<<<n_tiles, 256, 0, st>>>(q, n32, tiles, consts, q, 0, nullptr);
         PB_LAUNCHED(ctx);
     }
     cudaError_t e = cudaMemcpyAsync(ctx->pinned, total, 32, cudaMemcpyDeviceToHost, st);
@@ -270,3 +274,38 @@ extern "C" int pb200_kzg_witness_dev(pb200_ctx *ctx, const uint64_t *poly_dev, s
     memcpy(eval_mont_out, ctx->pinned, 32);
     return 0;
 }
+
+// ---- sliced witness for the sharded prover (one process per GPU): rank r holds coefficients [lo, lo + cnt) of p(X) and needs
+// the same slice of q(X) = (p(X) − p(z)) / (X − z) for its share of the commitment.  q_i = z^{−(i+1)}·Σ_{j>i} a_j z^j splits into
+// the sum inside the slice (local scan) plus the total of every later slice — 32 bytes per rank, exchanged by the caller between
+// the two phases.  `work` must hold 5 + ⌈cnt / 1024⌉ scalars (z | consts[3] | slice total | tile sums) and is owned by the caller.
+int kzg_witness_slice_phase1(pb200_ctx *ctx, const uint64_t *poly_slice_dev, uint32_t lo, uint32_t cnt, const uint64_t z_mont[4],
+                             uint64_t *q_slice_dev, uint64_t *work_dev, uint64_t slice_total_out[4]) {
+    const uint32_t n_tiles = (cnt + kFrScanTile - 1) / kFrScanTile;
+    Fr *zd = (Fr *)work_dev, *consts = zd + 1, *total = zd + 4, *tiles = zd + 5;
+    cudaStream_t st = ctx->stream;
+    PB_CUDA(ctx, cudaMemcpyAsync(zd, z_mont, 32, cudaMemcpyHostToDevice, st));
+    witness_consts_kernel<<<1, 1, 0, st>>>(zd, consts);
+    PB_LAUNCHED(ctx);
+    witness_scale_kernel<<<(cnt + 1023) / 1024, 256, 0, st>>>((const Fr *)poly_slice_dev, (Fr *)q_slice_dev, cnt, consts, lo);
+    PB_LAUNCHED(ctx);
+    fr_scan_tile_sums_kernel<<<n_tiles, 256, 0, st>>>((const Fr *)q_slice_dev, cnt, tiles);
+    PB_LAUNCHED(ctx);
+    fr_scan_top_kernel<<<1, 256, 0, st>>>(tiles, n_tiles, total);
+    PB_LAUNCHED(ctx);
+    PB_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, total, 32, cudaMemcpyDeviceToHost, st));
+    PB_CUDA(ctx, cudaStreamSynchronize(st));
+    memcpy(slice_total_out, ctx->pinned, 32);
+    return 0;
+}
+int kzg_witness_slice_phase2(pb200_ctx *ctx, uint32_t lo, uint32_t cnt, uint64_t *q_slice_dev, uint64_t *work_dev,
+                             const uint64_t later_slices_total[4]) {
+    const uint32_t n_tiles = (cnt + kFrScanTile - 1) / kFrScanTile;
+    Fr *zd = (Fr *)work_dev, *consts = zd + 1, *total = zd + 4, *tiles = zd + 5;
+    cudaStream_t st = ctx->stream;
+    PB_CUDA(ctx, cudaMemcpyAsync(total, later_slices_total, 32, cudaMemcpyHostToDevice, st));   // the slot is free again: reuse it for the carry
+    witness_finish_kernel<<<n_tiles, 256, 0, st>>>((const Fr *)q_slice_dev, cnt, tiles, consts, (Fr *)q_slice_dev, lo, total);
+    PB_LAUNCHED(ctx);
+    return 0;
+}
+size_t kzg_witness_slice_work_scalars(uint32_t cnt) { return 5 + (cnt + kFrScanTile - 1) / kFrScanTile; }

@@ -1168,12 +1168,39 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
             }
         }
         A.terms = k;
+        uint64_t point[4], unused[4];
+        (which == 0 ? z : zw).store(point);
+        const bool z_zero = (point[0] | point[1] | point[2] | point[3]) == 0;
+        if (world > 1 && !z_zero && kzg_witness_slice_work_scalars((uint32_t)pk->slice_n) <= n / 2) {
+            // Sharded: this rank only needs its coefficient slice of the witness (its share of the commitment).  Linear
+            // combination over the slice, local suffix scan, and the totals of the later slices (32 bytes per rank) as carry.
+            const uint32_t lo = (uint32_t)pk->slice_lo, cnt = (uint32_t)pk->slice_n;
+            for (int t = 0; t < k; t++) {
+                A.p[t] += lo;
+                A.len[t] = cnt;
+            }
+            A.n = cnt;
+            A.out = pk->agg + lo;
+            lincomb_kernel<<<cdiv(cnt, 256), 256, 0, st>>>(A);
+            PB_LAUNCHED(ctx);
+            Fr *q_slice = pk->wit + (size_t)which * n + lo;
+            uint64_t *work = (uint64_t *)(pk->num + (size_t)which * (n / 2));   // round-2 scratch, free by now: ≥ 5 + cnt/1024 scalars
+            uint64_t mine[4];
+            PB_TRY(kzg_witness_slice_phase1(ctx, (const uint64_t *)(pk->agg + lo), lo, cnt, point, (uint64_t *)q_slice, work, mine));
+            std::vector<uint64_t> all((size_t)world * 4);
+            if (pk->shard.allgather(pk->shard.user, mine, all.data(), 32) != 0)
+                return pb_fail(ctx, PB200_ERR_ARG, "sharded witness", "the all-gather callback failed", __FILE__, __LINE__);
+            HFr later = HFr::zero();
+            for (uint32_t r = pk->shard.rank + 1; r < world; r++) later = later + HFr::load(&all[(size_t)r * 4]);
+            uint64_t carry[4];
+            later.store(carry);
+            PB_TRY(kzg_witness_slice_phase2(ctx, lo, cnt, (uint64_t *)q_slice, work, carry));
+            continue;
+        }
         A.n = n32;
         A.out = pk->agg;
         lincomb_kernel<<<cdiv(n, 256), 256, 0, st>>>(A);
         PB_LAUNCHED(ctx);
-        uint64_t point[4], unused[4];
-        (which == 0 ? z : zw).store(point);
         PB_TRY(pb200_kzg_witness_dev(ctx, (const uint64_t *)pk->agg, n, point, (uint64_t *)(pk->wit + (size_t)which * n), unused));
     }
     // the second challenge is squeezed before either witness is committed, so both commitments are one batched MSM

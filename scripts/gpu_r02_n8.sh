@@ -3,6 +3,6 @@
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 5 --warmup 3 \
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 8 --steps 10 --warmup 3 \
   > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err
 echo "bench n8 rc=$?"; grep -v OMP gpurun_out/r02_bench_n8.err | tail -c 1500; head -c 7000 gpurun_out/r02_bench_n8.json
