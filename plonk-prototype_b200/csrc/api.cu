@@ -35,8 +35,6 @@ extern "C" int pb200_init(pb200_ctx **out, int device_id) {
     *out = ctx;
     PB_CUDA(ctx, cudaSetDevice(device_id));
     PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    PB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
-    for (auto &e : ctx->aux_ev) PB_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     {   // keep freed stream-ordered allocations in the pool instead of returning them to the driver
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
@@ -54,17 +52,12 @@ extern "C" void pb200_destroy(pb200_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     pb200_comm_destroy(ctx);
     ntt_free_plans(ctx);
     if (ctx->msm_ws) cudaFree(ctx->msm_ws);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
-    for (auto &e : ctx->aux_ev)
-        if (e) cudaEventDestroy(e);
-    if (ctx->ntt_scratch_aux) cudaFree(ctx->ntt_scratch_aux);
     delete ctx;
 }
 extern "C" const char *pb200_last_error(const pb200_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }

@@ -27,12 +27,6 @@ struct pb200_ctx {
     std::map<uint32_t, NttPlan *> ntt_plans;  // key: log_n | inverse << 8 | coset << 9
     void *ntt_scratch = nullptr;
     size_t ntt_scratch_bytes = 0;
-    // auxiliary stream: the prover's challenge-independent coset transforms run here, concurrently with the commitment of the
-    // same round on `stream` (their CTAs fit beside the MSM kernels' and use issue slots those leave idle)
-    cudaStream_t aux_stream = nullptr;
-    cudaEvent_t aux_ev[6] = {};
-    void *ntt_scratch_aux = nullptr;
-    size_t ntt_scratch_aux_bytes = 0;
     // MSM workspace (grown on demand, reused across calls)
     void *msm_ws = nullptr;
     size_t msm_ws_bytes = 0;
@@ -87,8 +81,8 @@ struct PbTimer {
     pb200_ctx *ctx;
     const char *name;
     cudaEvent_t a = nullptr, b = nullptr;
-    PbTimer(pb200_ctx *c, const char *n, bool enable = true) : ctx(c), name(n) {
-        if (ctx->profile && enable) {
+    PbTimer(pb200_ctx *c, const char *n) : ctx(c), name(n) {
+        if (ctx->profile) {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
             cudaEventRecord(a, ctx->stream);
@@ -118,8 +112,6 @@ struct PbTimer {
 };
 
 int pb_ensure(pb200_ctx *ctx, void **buf, size_t *have, size_t need);  // api.cu
-// ntt.cu: pb200_ntt_batch_dev on the context's auxiliary stream (own scratch buffer; no profiling timer)
-int ntt_batch_on_aux(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, uint32_t batch, int inverse, int coset);
 int comm_allgather_host(pb200_ctx *ctx, const void *send, void *recv, size_t bytes);  // comm.cu
 int comm_stream_barrier(pb200_ctx *ctx);                                              // comm.cu
 // Σ over ranks of `batch` projective points each rank holds in comm_partials_buffer(): all-gather + add on the device, one D2H

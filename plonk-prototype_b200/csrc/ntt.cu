@@ -522,8 +522,7 @@ static size_t ntt_tma_smem_bytes(uint32_t S) {
     return 1024 + ((size_t)32 << (S + 2)) + (((size_t)ntt_tw_image_entries(S) * sizeof(Fr) + 15) & ~(size_t)15) + 16;
 }
 // One pass over `nb` vectors of 2^L scalars (src / dst point at the first of them).
-static int ntt_launch_tma(pb200_ctx *ctx, cudaStream_t st, const NttPassTma &tp, const Fr *src, Fr *dst, uint32_t L, uint32_t blocks,
-                          uint32_t nb) {
+static int ntt_launch_tma(pb200_ctx *ctx, const NttPassTma &tp, const Fr *src, Fr *dst, uint32_t L, uint32_t blocks, uint32_t nb) {
     // measured on B200 (profiles/ntt_sweep_r02.json): 512 threads per SM at 128 registers and 384 at ≤ 168 tie up to S = 8
     // (2^24: 3.40 ms both) and the wide variant loses at S = 9, where it leaves one CTA per SM (2^26: 17.1 vs 14.4 ms)
     static const char *regs_env = getenv("PB200_NTT_TMA_REGS");
@@ -540,16 +539,13 @@ static int ntt_launch_tma(pb200_ctx *ctx, cudaStream_t st, const NttPassTma &tp,
     }
     NttTmaKernel k = ntt_tma_kernel_for(tp.S, wide_regs);
     PB_ARG(ctx, k != nullptr);
-    k<<<dim3(blocks, nb), 1u << (tp.S - 1), ntt_tma_smem_bytes(tp.S), st>>>(map_in, map_out, src, tp);
+    k<<<dim3(blocks, nb), 1u << (tp.S - 1), ntt_tma_smem_bytes(tp.S), ctx->stream>>>(map_in, map_out, src, tp);
     PB_LAUNCHED(ctx);
     return 0;
 }
 
-// aux = true: launch on the context's auxiliary stream with its own scratch buffer (plonk.cu overlaps these transforms with
-// the MSM of the same round); the plan tables are built on the main stream, so a plan built by this very call is waited for.
-static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset, uint32_t batch = 1, bool aux = false) {
+static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset, uint32_t batch = 1) {
     if (L == 0) return 0;  // a one-point domain: every variant is the identity map
-    cudaStream_t st = aux ? ctx->aux_stream : ctx->stream;
     NttPlan *pl = nullptr;
     auto it = ctx->ntt_plans.find(L | ((uint32_t)inverse << 8) | ((uint32_t)coset << 9));
     if (it != ctx->ntt_plans.end()) {
@@ -561,32 +557,19 @@ static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset,
             return rc;
         }
         ctx->ntt_plans[L | ((uint32_t)inverse << 8) | ((uint32_t)coset << 9)] = pl;
-        if (aux) PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    PbTimer timer(ctx, "ntt.total", !aux);   // (transforms on the auxiliary stream are not timed)
+    PbTimer timer(ctx, "ntt.total");
     if (pl->n_pass == 0) {
         for (uint32_t b = 0; b < batch; b++) {
-            ntt_tiny_kernel<<<1, 1, 0, st>>>(data + ((size_t)b << L), L, inverse, coset, pl->consts);
+            ntt_tiny_kernel<<<1, 1, 0, ctx->stream>>>(data + ((size_t)b << L), L, inverse, coset, pl->consts);
             PB_LAUNCHED(ctx);
         }
     } else {
         const size_t bytes = (sizeof(Fr) << L) * batch;
         Fr *scratch = nullptr;
         if (pl->n_pass > 1) {
-            if (aux) {
-                if (ctx->ntt_scratch_aux_bytes < bytes) {   // (pb_ensure synchronises the main stream; this buffer belongs to the other one)
-                    PB_CUDA(ctx, cudaStreamSynchronize(ctx->aux_stream));
-                    if (ctx->ntt_scratch_aux) PB_CUDA(ctx, cudaFree(ctx->ntt_scratch_aux));
-                    ctx->ntt_scratch_aux = nullptr;
-                    ctx->ntt_scratch_aux_bytes = 0;
-                    PB_CUDA(ctx, cudaMalloc(&ctx->ntt_scratch_aux, bytes));
-                    ctx->ntt_scratch_aux_bytes = bytes;
-                }
-                scratch = (Fr *)ctx->ntt_scratch_aux;
-            } else {
-                PB_TRY(pb_ensure(ctx, &ctx->ntt_scratch, &ctx->ntt_scratch_bytes, bytes));
-                scratch = (Fr *)ctx->ntt_scratch;
-            }
+            PB_TRY(pb_ensure(ctx, &ctx->ntt_scratch, &ctx->ntt_scratch_bytes, bytes));
+            scratch = (Fr *)ctx->ntt_scratch;
         }
         for (int i = 0; i < pl->n_pass; i++) {
             const NttPass &p = pl->pass[i];
@@ -605,23 +588,20 @@ static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset,
                 if (pl->tma && !force_legacy) {
                     NttPassTma tp = pl->tpass[i];
                     tp.batch_log = L;
-                    PB_TRY(ntt_launch_tma(ctx, st, tp, src + ((size_t)b0 << L), dst + ((size_t)b0 << L), L, blocks, nb));
+                    PB_TRY(ntt_launch_tma(ctx, tp, src + ((size_t)b0 << L), dst + ((size_t)b0 << L), L, blocks, nb));
                     continue;
                 }
-                ntt_pass_kernel<<<dim3(blocks, nb), threads, smem, st>>>(src + ((size_t)b0 << L), dst + ((size_t)b0 << L), pb);
+                ntt_pass_kernel<<<dim3(blocks, nb), threads, smem, ctx->stream>>>(src + ((size_t)b0 << L), dst + ((size_t)b0 << L), pb);
                 PB_LAUNCHED(ctx);
             }
         }
     }
     timer.stop();
-    if (ctx->profile && !aux) {
+    if (ctx->profile) {
         PB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         timer.collect();
     }
     return 0;
-}
-int ntt_batch_on_aux(pb200_ctx *ctx, uint64_t *data_dev, uint32_t log_n, uint32_t batch, int inverse, int coset) {
-    return ntt_run(ctx, (Fr *)data_dev, log_n, inverse ? 1 : 0, coset ? 1 : 0, batch, true);
 }
 
 int ntt_module_init(pb200_ctx *ctx) {

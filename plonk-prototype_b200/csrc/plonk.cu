@@ -533,11 +533,10 @@ int commit_bytes(pb200_ctx *ctx, const pb200_srs *srs, const pb200_prover_key *p
     return commit_bytes_batch(ctx, srs, pk, poly, n, 1, n, out);
 }
 
-int coset_extend(pb200_ctx *ctx, Fr *dst, const Fr *src, uint32_t n, uint32_t log_n4, uint32_t batch, bool aux = false) {
+int coset_extend(pb200_ctx *ctx, Fr *dst, const Fr *src, uint32_t n, uint32_t log_n4, uint32_t batch) {
     const uint32_t N4 = 1u << log_n4;
-    pad_copy_kernel<<<dim3(cdiv(N4, 256), batch), 256, 0, aux ? ctx->aux_stream : ctx->stream>>>(dst, src, n, N4);
+    pad_copy_kernel<<<dim3(cdiv(N4, 256), batch), 256, 0, ctx->stream>>>(dst, src, n, N4);
     PB_LAUNCHED(ctx);
-    if (aux) return ntt_batch_on_aux(ctx, (uint64_t *)dst, log_n4, batch, 0, 1);
     return pb200_ntt_batch_dev(ctx, (uint64_t *)dst, log_n4, batch, 0, 1);
 }
 
@@ -580,11 +579,7 @@ struct RoundClock {
 
 extern "C" void pb200_prover_key_free(pb200_ctx *ctx, pb200_prover_key *pk) {
     if (!pk) return;
-    if (ctx) {
-        cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);       // a failed prove may have left work of either stream in flight
-        cudaStreamSynchronize(ctx->aux_stream);
-    }
+    if (ctx) cudaSetDevice(ctx->device);
     for (uint32_t h = 0; h < 8; h++)
         if (pk->peer_slab[h] && h != pk->shard.rank) cudaIpcCloseMemHandle(pk->peer_slab[h]);
     cudaFree(pk->slab);
@@ -816,23 +811,6 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
     PB_LAUNCHED(ctx);
     PB_CUDA(ctx, cudaMemcpyAsync(pk->w_poly, pk->w_evals, 4 * n * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
     PB_TRY(pb200_ntt_batch_dev(ctx, (uint64_t *)pk->w_poly, log_n, 4, 1, 0));
-    // Round 3 needs a, b, c, d, z and PI on the 4n coset — none of which depends on a challenge squeezed after the polynomial
-    // exists.  On a single GPU those six coset transforms run on the auxiliary stream while the main stream commits (their
-    // CTAs co-reside with the MSM kernels' and fill issue slots the accumulation leaves idle); round 3 waits for their events.
-    static const bool no_overlap = getenv("PB200_PROVE_NO_OVERLAP") != nullptr;   // measurement switch
-    const uint32_t world_r1 = pk->shard.world;
-    uint32_t log_g_r1 = 0;
-    while ((1u << log_g_r1) < world_r1) log_g_r1++;
-    const bool sharded_round3 = world_r1 > 1 && pk->shard.alltoall_dev && pk->shard.allgather_dev && log_n + 2 >= 8 + log_g_r1 + 2 &&
-                                !(pk->q_nonzero[Q_LOGIC] || pk->q_nonzero[Q_FIXED] || pk->q_nonzero[Q_VAR]);
-    const bool overlap = !sharded_round3 && !no_overlap;
-    Fr *const w4_buf = pk->ev4, *const z4_buf = pk->ev4 + 4 * N4, *const pi4_buf = pk->ev4 + 5 * N4;
-    if (overlap) {
-        PB_CUDA(ctx, cudaEventRecord(ctx->aux_ev[0], st));                      // w_poly is ready
-        PB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[0], 0));
-        PB_TRY(coset_extend(ctx, w4_buf, pk->w_poly, n32, log_n + 2, 4, true));
-        PB_CUDA(ctx, cudaEventRecord(ctx->aux_ev[1], ctx->aux_stream));         // a, b, c, d on the coset
-    }
     const char *const w_label[4] = {"w_l", "w_r", "w_o", "w_4"};
     PB_TRY(commit_bytes_batch(ctx, srs, pk, pk->w_poly, n, 4, n, P));
     for (int c = 0; c < 4; c++) tr.append_commitment(w_label[c], P + 48 * c);
@@ -852,12 +830,6 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
     perm_finish_kernel<<<cdiv(n, 256), 256, 0, st>>>(pk->num, pk->den, scal + 2, n32, pk->z_poly);
     PB_LAUNCHED(ctx);
     PB_TRY(pb200_ntt_dev(ctx, (uint64_t *)pk->z_poly, log_n, 1, 0));
-    if (overlap) {
-        PB_CUDA(ctx, cudaEventRecord(ctx->aux_ev[2], st));                      // z_poly is ready
-        PB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ev[2], 0));
-        PB_TRY(coset_extend(ctx, z4_buf, pk->z_poly, n32, log_n + 2, 1, true));
-        PB_CUDA(ctx, cudaEventRecord(ctx->aux_ev[3], ctx->aux_stream));
-    }
     PB_TRY(commit_bytes(ctx, srs, pk, pk->z_poly, n, P + 48 * 4));
     tr.append_commitment("z", P + 48 * 4);
     clk.lap("prove.round2");
@@ -911,17 +883,12 @@ static int prove_impl(pb200_ctx *ctx, const pb200_srs *srs, pb200_prover_key *pk
     uint32_t log_g = 0;
     while ((1u << log_g) < world) log_g++;
     // (the sharded layout transforms z(ωX) and d(ωX) only: circuits with ECC / logic rows keep round 3 replicated)
-    const bool dist3 = sharded_round3;   // (decided before round 1: world > 1, device collectives present, domain large enough, no ECC / logic rows)
+    const bool dist3 = world > 1 && pk->shard.alltoall_dev && pk->shard.allgather_dev && log_n4 >= 8 + log_g + 2 && !extra;
     if (!dist3) {
         // coset evaluations on 4n: a, b, c, d | z | pi   (L₁ is kept from preprocessing)
-        Fr *w4 = w4_buf, *z4 = z4_buf, *pi4 = pi4_buf;
-        if (overlap) {
-            PB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->aux_ev[1], 0));   // a, b, c, d: started in round 1
-            PB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->aux_ev[3], 0));   // z: started in round 2
-        } else {
-            PB_TRY(coset_extend(ctx, w4, pk->w_poly, n32, log_n4, 4));
-            PB_TRY(coset_extend(ctx, z4, pk->z_poly, n32, log_n4, 1));
-        }
+        Fr *w4 = pk->ev4, *z4 = pk->ev4 + 4 * N4, *pi4 = z4 + N4;
+        PB_TRY(coset_extend(ctx, w4, pk->w_poly, n32, log_n4, 4));
+        PB_TRY(coset_extend(ctx, z4, pk->z_poly, n32, log_n4, 1));
         PB_TRY(coset_extend(ctx, pi4, pk->pi_poly, n32, log_n4, 1));
         A.w = w4;
         A.z = z4;
