@@ -203,12 +203,13 @@ def run_reference(args, rank, world):
     L = args.log_gates
     budget = float(os.environ.get("PB200_REF_BUDGET_S", "780"))
     t_start = time.perf_counter()
-    # calibrate on 2^14 gates (also the warm-up: pages in the library and the thread pool; CPU code has no other warm state)
-    cal_log = min(L, 14)
+    # calibrate on 2^16 gates (also the warm-up: pages in the library and the thread pool; CPU code has no other warm state).
+    # Linear extrapolation is conservative: the per-gate cost of the CPU prover falls with the size (Pippenger windows grow).
+    cal_log = min(L, 16)
     _, _, cal_pre, cal_prove = cpu_prove(cal_log, cores)
     for _ in range(max(args.warmup - 1, 0)):
         cpu_prove(min(L, 12), cores)
-    scale = float(1 << (L - cal_log)) * 1.15
+    scale = float(1 << (L - cal_log))
     sample_log = L
     while sample_log > 12 and (cal_pre + args.steps * cal_prove) * scale * 2.0 ** (sample_log - L) > budget - (time.perf_counter() - t_start):
         sample_log -= 1
