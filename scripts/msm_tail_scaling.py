@@ -14,7 +14,7 @@ import plonk_prototype_b200 as pb  # noqa: E402
 
 ctx = pb.Context(0)
 out = []
-for log_n in (20, 19, 18, 17, 16):
+for log_n in ([int(v) for v in sys.argv[1:]] or [20, 19, 18, 17, 16]):
     n = 1 << log_n
     pp = pb.PublicParameters(n - 1, 0xB2 + log_n, ctx)
     for batch in (4, 1):
