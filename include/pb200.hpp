@@ -121,6 +121,63 @@ class EvaluationDomain {
     uint32_t log_n_;
 };
 
+// ---- Polynomial / Evaluations (dusk-plonk 0.8.2 fft::{Polynomial, Evaluations}) ------------------
+// Dense coefficient form, lowest degree first, no zero coefficients at the top.  evaluate / ruffini run on the GPU
+// (pb200_kzg_witness_dev: value and quotient by X − z come out of the same Ruffini pass).
+class Polynomial {
+  public:
+    std::vector<BlsScalar> coeffs;
+    static Polynomial zero() { return Polynomial(); }
+    static Polynomial from_coefficients_vec(std::vector<BlsScalar> c) {
+        while (!c.empty() && c.back() == BlsScalar::zero()) c.pop_back();  // truncate_leading_zeros
+        Polynomial p;
+        p.coeffs = std::move(c);
+        return p;
+    }
+    static Polynomial from_coefficients_slice(const BlsScalar *c, size_t n) { return from_coefficients_vec(std::vector<BlsScalar>(c, c + n)); }
+    bool is_zero() const { return coeffs.empty(); }
+    size_t degree() const { return coeffs.empty() ? 0 : coeffs.size() - 1; }  // 0 for the zero polynomial, like upstream
+    size_t len() const { return coeffs.size(); }
+    BlsScalar evaluate(Context &ctx, const BlsScalar &point) const {
+        if (is_zero()) return BlsScalar::zero();
+        BlsScalar ev;
+        ruffini_dev(ctx, point, nullptr, &ev);
+        return ev;
+    }
+    // (p(X) − p(z)) / (X − z)
+    Polynomial ruffini(Context &ctx, const BlsScalar &z) const {
+        if (is_zero()) return zero();
+        std::vector<BlsScalar> q(coeffs.size());
+        BlsScalar ev;
+        ruffini_dev(ctx, z, q.data(), &ev);
+        q.pop_back();  // the library writes n scalars, the top one zero
+        return from_coefficients_vec(std::move(q));
+    }
+
+  private:
+    void ruffini_dev(Context &ctx, const BlsScalar &z, BlsScalar *quotient, BlsScalar *ev) const {
+        const size_t bytes = coeffs.size() * sizeof(BlsScalar);
+        void *d_p = nullptr, *d_q = nullptr;
+        ctx.check(pb200_malloc(ctx.raw(), &d_p, bytes), "pb200_malloc");
+        int rc = pb200_malloc(ctx.raw(), &d_q, bytes);
+        if (rc == 0) rc = pb200_h2d(ctx.raw(), d_p, coeffs.data(), bytes);
+        if (rc == 0) rc = pb200_kzg_witness_dev(ctx.raw(), static_cast<const uint64_t *>(d_p), coeffs.size(), z.v.l, static_cast<uint64_t *>(d_q), ev->v.l);
+        if (rc == 0 && quotient) rc = pb200_d2h(ctx.raw(), quotient, d_q, bytes);
+        pb200_free(ctx.raw(), d_p);
+        if (d_q) pb200_free(ctx.raw(), d_q);
+        ctx.check(rc, "pb200_kzg_witness_dev");
+    }
+};
+// Values over a whole domain; interpolate() = ifft + truncate.
+class Evaluations {
+  public:
+    std::vector<BlsScalar> evals;
+    EvaluationDomain domain;
+    static Evaluations from_vec_and_domain(std::vector<BlsScalar> evals, const EvaluationDomain &domain) { return Evaluations{std::move(evals), domain}; }
+    Polynomial interpolate_by_ref() const { return Polynomial::from_coefficients_vec(domain.ifft(evals)); }
+    Polynomial interpolate() const { return interpolate_by_ref(); }
+};
+
 // ---- G1 / MSM / KZG --------------------------------------------------------------------------------------------
 struct G1Affine {
     uint64_t x[6], y[6];  // Montgomery; the identity is not representable (an SRS never holds it)
@@ -168,6 +225,7 @@ class CommitKey {
         ctx_->check(pb200_msm_g1(ctx_->raw(), srs_, 0, reinterpret_cast<const uint64_t *>(coeffs.data()), coeffs.size(), out.xyz), "pb200_msm_g1");
         return out;
     }
+    G1Projective commit(const Polynomial &p) const { return commit(p.coeffs); }
     pb200_srs *raw() const { return srs_; }
 
   private:

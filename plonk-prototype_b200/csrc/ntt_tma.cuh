@@ -71,6 +71,15 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// Read-only global load the compiler must leave where it is written (volatile): used to issue table loads a whole
+// multiplication ahead of their use — plain C++ loads were scheduled right in front of the consuming multiply, and the ncu
+// of the first version showed the full L2 / DRAM latency of each of the eight inter-pass twiddles as long-scoreboard stall.
+__device__ __forceinline__ Fr ldg_fr_pinned(const Fr *p) {
+    Fr r;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]) : "l"(p));
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4+16];" : "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7]) : "l"(p));
+    return r;
+}
 // byte offset of the low half of scalar (x, c) inside the tile; the high half is at offset ^ 16
 __device__ __forceinline__ uint32_t tile_off(uint32_t x, uint32_t c) { return (x << 7) + ((((c << 1)) ^ (x & 7u)) << 4); }
 __device__ __forceinline__ Fr lds_fr(uint32_t addr) {
@@ -174,8 +183,8 @@ ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
         // rows are contiguous in global memory but the tile is point-major: stage through registers (coalesced 128-bit loads)
         const Fr *src = in + ((uint64_t)b << p.batch_log);
         const uint32_t n2_log = p.nrows_log - p.n1_log;
-#pragma unroll 2
-        for (uint32_t i = tid; i < T; i += NTHR) {
+#pragma unroll
+        for (uint32_t i = tid; i < T; i += NTHR) {   // T / NTHR = 8 iterations, fully unrolled: sixteen 128-bit loads in flight
             const uint32_t x = i & ((1u << S) - 1), cc = i >> S;
             const uint32_t rr = rowrev0 + cc;
             const uint32_t row = ((rr & ((1u << p.n1_log) - 1)) << n2_log) + (rr >> p.n1_log);
@@ -201,11 +210,15 @@ ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     __syncthreads();
     if (p.load_mode == 2) {   // coset_fft: a_j ← a_j·7^j on the way in (one multiplier instance, its own sweep over the tile)
         const Fr *lf = p.l_full + in_base;
+        Fr f_next = tma::ldg_fr_pinned(lf + (((uint64_t)(tid >> 2) << p.ncol_log) + (tid & 3u)));
 #pragma unroll 1
         for (uint32_t i = tid; i < T; i += NTHR) {
             const uint32_t x = i >> 2, cc = i & 3u;
             const uint32_t off = tile + tma::tile_off(x, cc);
-            tma::sts_fr(off, tma::lds_fr(off) * g_load(lf + (((uint64_t)x << p.ncol_log) + cc)));
+            const Fr f = f_next;
+            const uint32_t i2 = min(i + NTHR, T - 1);   // the factor of the next iteration travels during this multiply
+            f_next = tma::ldg_fr_pinned(lf + (((uint64_t)(i2 >> 2) << p.ncol_log) + (i2 & 3u)));
+            tma::sts_fr(off, tma::lds_fr(off) * f);
         }
         __syncthreads();
     }
@@ -243,6 +256,27 @@ ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
 #pragma unroll
     for (int e = 0; e < 8; e++) a[e] = tma::lds_fr(tile + tma::tile_off((tx_rev << 3) | (uint32_t)e, c));
     __syncthreads();   // every thread has read its rows: they may now be overwritten with outputs of other rows
+    // Output row of a[e] and the address of its inter-pass twiddle / coset factor.  The factors come from a table as long as
+    // the vector (L2 at best, DRAM on the first pass): PF of them are always in flight — the first PF are requested here, before
+    // the last round's butterflies, the others PF − 1 multiplications before their use.
+    constexpr int PF = THREADS_PER_SM >= 512 ? 2 : 4;
+    const uint32_t k_hi = tx;   // k = brev_S((tx_rev << 3) | e) = (brev3(e) << (S−3)) | brev_{S−3}(tx_rev) = … | tx
+    auto out_row = [&](int e) -> uint32_t {
+        const uint32_t e_rev = ((e & 1) << 2) | (e & 2) | ((e >> 2) & 1);
+        return (e_rev << (S - 3)) | k_hi;
+    };
+    auto factor_at = [&](int e) -> const Fr * {   // 4: inter-pass twiddle full[(k << ncol_log) + col] | 5: coset factor full[natural output index]
+        const uint32_t k = out_row(e);
+        const uint64_t idx = p.store_mode == 4 ? (((uint64_t)k << p.ncol_log) + col0 + c)
+                                               : ((uint64_t)(rowrev0 + c) + ((uint64_t)k << p.nrows_log));
+        return p.s_full + idx;
+    };
+    constexpr bool EARLY = !(S == 6 && THREADS_PER_SM >= 512);   // (that one variant would spill four registers)
+    Fr f[PF];
+    if (EARLY && p.store_mode) {
+#pragma unroll
+        for (int e = 0; e < PF; e++) f[e] = tma::ldg_fr_pinned(factor_at(e));
+    }
     if (b_top >= 2) {
         bfly1(a[0], a[4]);
 #pragma unroll
@@ -257,21 +291,21 @@ ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
     }
 #pragma unroll
     for (int e = 0; e < 8; e += 2) bfly1(a[e], a[e + 1]);
-    // bit reversal + inter-pass twiddle / coset factor in registers, then to the tile at the OUTPUT row k
-    {
-        const uint32_t k_hi = tx;   // k = brev_S((tx_rev << 3) | e) = (brev3(e) << (S−3)) | brev_{S−3}(tx_rev) = … | tx
+    // bit reversal + factor in registers, then to the tile at the OUTPUT row k
+    if (p.store_mode) {
+        if (!EARLY) {
+#pragma unroll
+            for (int e = 0; e < PF; e++) f[e] = tma::ldg_fr_pinned(factor_at(e));
+        }
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const uint32_t e_rev = ((e & 1) << 2) | (e & 2) | ((e >> 2) & 1);
-            const uint32_t k = (e_rev << (S - 3)) | k_hi;
-            Fr val = a[e];
-            if (p.store_mode) {   // 4: inter-pass twiddle full[(k << ncol_log) + col] | 5: coset factor full[natural output index]
-                const uint64_t idx = p.store_mode == 4 ? (((uint64_t)k << p.ncol_log) + col0 + c)
-                                                       : ((uint64_t)(rowrev0 + c) + ((uint64_t)k << p.nrows_log));
-                val = val * g_load(p.s_full + idx);
-            }
-            tma::sts_fr(tile + tma::tile_off(k, c), val);
+            const Fr val = a[e] * f[e % PF];
+            if (e + PF < 8) f[e % PF] = tma::ldg_fr_pinned(factor_at(e + PF));
+            tma::sts_fr(tile + tma::tile_off(out_row(e), c), val);
         }
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++) tma::sts_fr(tile + tma::tile_off(out_row(e), c), a[e]);
     }
     tma::fence_proxy_async();   // generic-proxy writes above → visible to the async proxy (the tensor store)
     __syncthreads();

@@ -62,7 +62,8 @@ class CommitKey:
         return self.n - 1
 
     def commit(self, coeffs):
-        coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+        """`CommitKey::commit(&Polynomial)`; also takes the bare coefficient array."""
+        coeffs = np.ascontiguousarray(getattr(coeffs, "coeffs", coeffs), dtype=np.uint64).reshape(-1, 4)
         if coeffs.shape[0] > self.n:
             raise ValueError("PolynomialDegreeTooLarge")  # dusk-plonk `check_degree_is_within_bounds`
         return self.ctx.msm(self._srs, coeffs)
