@@ -127,6 +127,14 @@ PB200_API int pb200_msm_g1_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t offs
  * one after the other.  Blocks; results on the host. */
 PB200_API int pb200_msm_g1_batch_dev(pb200_ctx *ctx, const pb200_srs *srs, size_t offset, const uint64_t *scalars_mont_dev, size_t n,
                                      uint32_t batch, size_t scalar_stride, uint64_t *out_xyz_mont);
+/* dusk_bls12_381::multiscalar_mul::pippenger(points: impl Iterator<Item = G1Projective>, scalars: impl Iterator<Item =
+ * Scalar>) -> G1Projective — the iterator form next to msm_variable_base in the same upstream file (crate pinned at
+ * /root/reference/Cargo.toml:20; no caller in the reference or in dusk-plonk's prover).  Bases in
+ * homogeneous projective coordinates, n × (X ‖ Y ‖ Z) = n × 18 u64 Montgomery words on the HOST, Z = 0 for the identity;
+ * scalars n × 4 u64 Montgomery.  The bases are normalised on the device (one inversion per eight points) and summed by the
+ * same pipeline as pb200_msm_g1; the group element returned is the one upstream computes.  Blocks; result on the host. */
+PB200_API int pb200_pippenger_g1(pb200_ctx *ctx, const uint64_t *points_xyz_mont_host, const uint64_t *scalars_mont_host, size_t n,
+                                 uint64_t out_xyz_mont[18]);
 /* Sum of `count` projective points (each X ‖ Y ‖ Z, 18 × u64 Montgomery, HOST memory) — the combine step after
  * a point-range-sharded MSM: every rank's partial result is gathered and added here.
  * Output as for pb200_msm_g1. */

@@ -197,6 +197,7 @@ struct G1Projective {
     }
 };
 static_assert(sizeof(G1Affine) == 96, "packed affine point");
+static_assert(sizeof(G1Projective) == 144, "X ‖ Y ‖ Z");
 
 class CommitKey {
   public:
@@ -247,6 +248,16 @@ inline G1Projective msm_variable_base(Context &ctx, const std::vector<G1Affine> 
     const int rc = pb200_msm_g1(ctx.raw(), srs, 0, reinterpret_cast<const uint64_t *>(scalars.data()), scalars.size(), out.xyz);
     pb200_srs_free(ctx.raw(), srs);
     ctx.check(rc, "pb200_msm_g1");
+    return out;
+}
+
+// multiscalar_mul::pippenger(points, scalars): the iterator form over projective bases (Z = 0: the identity).
+inline G1Projective pippenger(Context &ctx, const std::vector<G1Projective> &points, const std::vector<BlsScalar> &scalars) {
+    if (points.size() != scalars.size()) throw Error("points and scalars differ in length");
+    G1Projective out;
+    ctx.check(pb200_pippenger_g1(ctx.raw(), reinterpret_cast<const uint64_t *>(points.data()), reinterpret_cast<const uint64_t *>(scalars.data()),
+                                 points.size(), out.xyz),
+              "pb200_pippenger_g1");
     return out;
 }
 

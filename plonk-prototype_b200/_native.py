@@ -18,7 +18,7 @@ EXPORTS = [
     "pb200_domain_log_size", "pb200_ntt", "pb200_ntt_dev", "pb200_ntt_batch_dev", "pb200_ntt_columns_dev", "pb200_ntt_columns_scatter_dev",
     "pb200_ipc_export", "pb200_ipc_open", "pb200_ipc_close", "pb200_block_transpose_dev",
     "pb200_srs_upload", "pb200_srs_wrap_dev", "pb200_srs_precompute", "pb200_srs_free", "pb200_srs_len",
-    "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_batch_dev", "pb200_g1_sum", "pb200_msm_window_bits",
+    "pb200_msm_g1", "pb200_msm_g1_dev", "pb200_msm_g1_batch_dev", "pb200_pippenger_g1", "pb200_g1_sum", "pb200_msm_window_bits",
     "pb200_srs_generate", "pb200_srs_generate_range", "pb200_srs_dev_ptr", "pb200_kzg_witness_dev", "pb200_fr_horner_step_dev",
     "pb200_preprocess", "pb200_preprocess_sharded", "pb200_prover_key_free", "pb200_prover_key_size", "pb200_prover_key_bytes", "pb200_prove", "pb200_prove_dev",
     "pb200_transcript_selftest", "pb200_synthetic_circuit", "pb200_verify", "pb200_opening_key_from_tau",
@@ -93,6 +93,7 @@ def lib():
         L.pb200_msm_g1_dev.argtypes = [vp, vp, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]
         L.pb200_msm_g1_batch_dev.argtypes = [vp, vp, ctypes.c_size_t, u64p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_size_t, u64p]
         L.pb200_g1_sum.argtypes = [vp, u64p, ctypes.c_size_t, u64p]
+        L.pb200_pippenger_g1.argtypes = [vp, u64p, u64p, ctypes.c_size_t, u64p]
         L.pb200_msm_window_bits.argtypes = [ctypes.c_size_t]
         L.pb200_msm_window_bits.restype = ctypes.c_uint32
         L.pb200_srs_generate.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.POINTER(vp)]
@@ -292,6 +293,15 @@ class Context:
     def msm_batch_dev(self, srs, scalars_dev, n, batch, stride, offset=0):
         out = np.zeros((batch, 18), np.uint64)
         self._check(lib().pb200_msm_g1_batch_dev(self._h, srs, offset, ctypes.c_void_p(scalars_dev), n, batch, stride, _ptr(out)))
+        return out
+
+    def pippenger(self, points_xyz_host, scalars_host):
+        """`multiscalar_mul::pippenger`: bases in projective coordinates (n, 18) u64, scalars (n, 4) u64, both Montgomery."""
+        pts = np.ascontiguousarray(points_xyz_host, dtype=np.uint64).reshape(-1, 18)
+        sc = np.ascontiguousarray(scalars_host, dtype=np.uint64).reshape(-1, 4)
+        assert pts.shape[0] == sc.shape[0]
+        out = np.zeros(18, np.uint64)
+        self._check(lib().pb200_pippenger_g1(self._h, _ptr(pts) if pts.size else None, _ptr(sc) if sc.size else None, pts.shape[0], _ptr(out)))
         return out
 
     def g1_sum(self, points_xyz_host):

@@ -577,6 +577,36 @@ extern "C" int pb200_msm_g1(pb200_ctx *ctx, const pb200_srs *srs, size_t offset,
     PB_CUDA(ctx, cudaMemcpyAsync(ctx->stage, scalars_mont_host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     return msm_run(ctx, srs, offset, (const uint64_t *)ctx->stage, n, out_xyz_mont);
 }
+// multiscalar_mul::pippenger(points: Iterator<G1Projective>, scalars: Iterator<Scalar>): the bases arrive in projective
+// coordinates; they are normalised on the device (one inversion per eight points) and summed by the same pipeline.
+extern "C" int pb200_pippenger_g1(pb200_ctx *ctx, const uint64_t *points_xyz_mont_host, const uint64_t *scalars_mont_host, size_t n,
+                                  uint64_t out_xyz_mont[18]) {
+    if (!ctx) return PB200_ERR_ARG;
+    PB_ARG(ctx, out_xyz_mont != nullptr);
+    if (n == 0) return msm_run(ctx, nullptr, 0, nullptr, 0, out_xyz_mont);
+    PB_ARG(ctx, points_xyz_mont_host != nullptr && scalars_mont_host != nullptr && n < ((size_t)1 << 32));
+    PB_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *dev = nullptr;   // [n × 144 B projective][n × 32 B scalars in][n × 96 B affine][n × 32 B scalars out]
+    PB_CUDA(ctx, cudaMalloc(&dev, n * (144 + 32 + 96 + 32)));
+    uint8_t *base = (uint8_t *)dev;
+    uint32_t *xyz = (uint32_t *)base;
+    uint64_t *sc_in = (uint64_t *)(base + n * 144), *sc_out = (uint64_t *)(base + n * (144 + 32 + 96));
+    G1Affine *aff = (G1Affine *)(base + n * (144 + 32));
+    int rc = 0;
+    cudaError_t e = cudaMemcpyAsync(xyz, points_xyz_mont_host, n * 144, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sc_in, scalars_mont_host, n * 32, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) rc = tail_g1_normalize(ctx, xyz, sc_in, n, aff, sc_out);
+    if (e == cudaSuccess && rc == 0) {
+        pb200_srs tmp;
+        tmp.dev = (const uint64_t *)aff;
+        tmp.n = n;
+        rc = msm_run(ctx, &tmp, 0, sc_out, n, out_xyz_mont);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(dev);
+    if (e != cudaSuccess) return pb_fail(ctx, PB200_ERR_CUDA, "pippenger", cudaGetErrorString(e), __FILE__, __LINE__);
+    return rc;
+}
 extern "C" int pb200_g1_sum(pb200_ctx *ctx, const uint64_t *points_xyz_mont_host, size_t count, uint64_t out_xyz_mont[18]) {
     if (!ctx) return PB200_ERR_ARG;
     PB_ARG(ctx, out_xyz_mont != nullptr && (points_xyz_mont_host != nullptr || count == 0) && count <= 4096);

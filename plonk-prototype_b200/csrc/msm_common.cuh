@@ -75,6 +75,7 @@ int tail_combine(pb200_ctx *ctx, const G1Xyzz *window_sums, MsmCfg cfg, G1Xyzz *
 int tail_batch_results(pb200_ctx *ctx, const G1Xyzz *set_sums, uint32_t batch, uint32_t *results);
 int tail_g1_sum(pb200_ctx *ctx, const uint32_t *pts, uint32_t count, uint32_t *result);
 int tail_g1_sum_batch(pb200_ctx *ctx, const uint32_t *pts, uint32_t count, uint32_t batch, uint32_t *results);
+int tail_g1_normalize(pb200_ctx *ctx, const uint32_t *xyz, const uint64_t *scalars_in, uint64_t n, G1Affine *out, uint64_t *scalars_out);
 int tail_precompute(pb200_ctx *ctx, const G1Affine *bases, uint32_t n, uint32_t c, uint32_t W, G1Affine *pre);
 int tail_synthetic_bases(pb200_ctx *ctx, G1Affine *out, uint64_t n, uint64_t a, uint64_t d);
 

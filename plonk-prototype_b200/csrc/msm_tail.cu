@@ -213,6 +213,55 @@ __global__ void __launch_bounds__(128) msm_precompute_kernel(const G1Affine *__r
 }
 
 
+// ------------------------------------------------------------------------------ projective bases (pippenger, iterator form)
+// Homogeneous projective (X:Y:Z) bases → packed affine, Montgomery's trick per thread: `per` points share one inversion.
+// A point with Z = 0 (the identity, which the affine layout cannot hold) becomes the generator with its scalar forced to
+// zero in the copy of the scalar vector the MSM then reads.
+__global__ void __launch_bounds__(128) g1_normalize_kernel(const uint32_t *__restrict__ xyz, const uint64_t *__restrict__ scalars_in,
+                                                           uint64_t n, G1Affine *out, uint64_t *scalars_out) {
+    constexpr uint32_t per = 8;
+    const uint64_t i0 = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * per;
+    if (i0 >= n) return;
+    const uint32_t cnt = (uint32_t)min((uint64_t)per, n - i0);
+    auto load_z = [&](uint32_t k) {
+        Fp z;
+        for (int w = 0; w < 12; w++) z.l[w] = xyz[36 * (i0 + k) + 24 + w];
+        return z;
+    };
+    Fp prefix[per];   // prefix[k] = Π_{j<k, Z_j ≠ 0} Z_j
+    Fp run = Fp::one();
+    for (uint32_t k = 0; k < cnt; k++) {
+        prefix[k] = run;
+        const Fp z = load_z(k);
+        if (!z.is_zero()) run = run * z;
+    }
+    Fp inv = run.inv();   // 1 / Π Z_j
+    for (int k = (int)cnt - 1; k >= 0; k--) {
+        const Fp z = load_z((uint32_t)k);
+        G1Affine a;
+        uint4 s0 = reinterpret_cast<const uint4 *>(scalars_in + 4 * (i0 + k))[0], s1 = reinterpret_cast<const uint4 *>(scalars_in + 4 * (i0 + k))[1];
+        if (z.is_zero()) {
+            const uint32_t gx[12] = {0xfd530c16u, 0x5cb38790u, 0x9976fff5u, 0x7817fc67u, 0x143ba1c1u, 0x154f95c7u,
+                                     0xf3d0e747u, 0xf0ae6acdu, 0x21dbf440u, 0xedce6eccu, 0x9e0bfb75u, 0x12017741u};
+            const uint32_t gy[12] = {0x0ce72271u, 0xbaac93d5u, 0x7918fd8eu, 0x8c22631au, 0x570725ceu, 0xdd595f13u,
+                                     0x50405194u, 0x51ac5829u, 0xad0059c0u, 0x0e1c8c3fu, 0x5008a26au, 0x0bbc3efcu};
+            for (int w = 0; w < 12; w++) { a.x.l[w] = gx[w]; a.y.l[w] = gy[w]; }
+            s0 = make_uint4(0, 0, 0, 0);
+            s1 = s0;
+        } else {
+            const Fp zi = inv * prefix[k];   // 1 / Z_k
+            inv = inv * z;
+            Fp X, Y;
+            for (int w = 0; w < 12; w++) { X.l[w] = xyz[36 * (i0 + k) + w]; Y.l[w] = xyz[36 * (i0 + k) + 12 + w]; }
+            a.x = X * zi;
+            a.y = Y * zi;
+        }
+        store_fp2(reinterpret_cast<uint4 *>(out + i0 + k), a.x, a.y);
+        reinterpret_cast<uint4 *>(scalars_out + 4 * (i0 + k))[0] = s0;
+        reinterpret_cast<uint4 *>(scalars_out + 4 * (i0 + k))[1] = s1;
+    }
+}
+
 }  // namespace
 
 // ---- launchers (declared in msm_common.cuh) -----------------------------------------------------------
@@ -264,6 +313,12 @@ int tail_synthetic_bases(pb200_ctx *ctx, G1Affine *out, uint64_t n, uint64_t a, 
     const uint32_t per = 32;
     const uint64_t threads = (n + per - 1) / per;
     synthetic_bases_kernel<<<(uint32_t)((threads + 127) / 128), 128, 0, ctx->stream>>>(out, n, a, d, per);
+    PB_LAUNCHED(ctx);
+    return 0;
+}
+int tail_g1_normalize(pb200_ctx *ctx, const uint32_t *xyz, const uint64_t *scalars_in, uint64_t n, G1Affine *out, uint64_t *scalars_out) {
+    const uint64_t threads = (n + 7) / 8;
+    g1_normalize_kernel<<<(uint32_t)((threads + 127) / 128), 128, 0, ctx->stream>>>(xyz, scalars_in, n, out, scalars_out);
     PB_LAUNCHED(ctx);
     return 0;
 }

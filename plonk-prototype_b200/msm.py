@@ -28,6 +28,13 @@ def msm_variable_base(points, scalars, ctx=None):
         ctx.srs_free(srs)
 
 
+def pippenger(points, scalars, ctx=None):
+    """`multiscalar_mul::pippenger(points, scalars)` — the iterator form over `G1Projective` bases (SURVEY.md §8a a13):
+    points an (n, 18) uint64 array X‖Y‖Z (Z = 0: the identity), scalars (n, 4); returns the projective sum like
+    `msm_variable_base`."""
+    return (ctx or default_context()).pippenger(points, scalars)
+
+
 _P = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
 _RP_INV = pow(1 << 384, -1, _P)
 

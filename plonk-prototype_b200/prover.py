@@ -10,6 +10,7 @@ Everything after synthesis — preprocessing and the five prover rounds — runs
 """
 import numpy as np
 
+from . import _native
 from .domain import default_context
 
 R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
@@ -227,6 +228,24 @@ class PublicParameters:
         self.srs = self.ctx.srs_generate(scalars_to_mont([tau]), self.n_points)
         if precompute and self.n_points <= (1 << 22):
             self.ctx.srs_precompute(self.srs)
+
+        self.beta_h = _native.opening_key_from_tau(scalars_to_mont([tau]))   # the opening key's β·H (G and H are the generators)
+
+    def to_raw_bytes(self):
+        """`PublicParameters::to_raw_bytes`: opening key (240 bytes) ‖ commit key (memory image of the points) — serial.py."""
+        from . import serial
+        return serial.opening_key_to_bytes(self.beta_h) + serial.commit_key_to_raw_bytes(self.ctx, self.srs)
+
+    @classmethod
+    def from_slice_unchecked(cls, data, ctx=None, precompute=True):
+        """`PublicParameters::from_slice_unchecked`: parameters cached with `to_raw_bytes` back onto the GPU."""
+        from . import serial
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        self.beta_h = serial.opening_key_from_bytes(bytes(data[:serial.OPENING_KEY_SIZE]))
+        self.srs = serial.commit_key_from_slice_unchecked(self.ctx, bytes(data[serial.OPENING_KEY_SIZE:]), precompute)
+        self.n_points = _native.lib().pb200_srs_len(self.srs)
+        return self
 
     def close(self):
         if self.srs is not None:

@@ -46,6 +46,10 @@ int main(int argc, char **argv) {
     printf("to_bytes %02x%02x%02x\n", bytes[0], bytes[1], bytes[2]);
     const auto red = BlsScalar::pow_of_2(70).reduce();
     printf("reduce %llx %llx\n", (unsigned long long)red[0], (unsigned long long)red[1]);
+    // fft::Polynomial: zero coefficients at the top are dropped, degree() of the zero polynomial is 0
+    const Polynomial p = Polynomial::from_coefficients_vec({BlsScalar::from(5), BlsScalar::zero(), BlsScalar::from(7), BlsScalar::zero(), BlsScalar::zero()});
+    const Polynomial pz = Polynomial::from_coefficients_vec({BlsScalar::zero(), BlsScalar::zero()});
+    printf("poly %zu %zu %d %zu %d\n", p.len(), p.degree(), (int)p.is_zero(), pz.degree(), (int)pz.is_zero());
     return 0;
 }
 

@@ -49,6 +49,7 @@ def test_cxx_composer_matches_python_mirror(tmp_path):
     assert lines["pi %d" % gate].split(" ")[2] == _limbs_hex(pb.scalars_to_mont([val])[0])
     assert lines["to_bytes"] == "to_bytes 341200"                      # little-endian canonical bytes of 0x1234
     assert lines["reduce"] == "reduce 0 40"                            # 2^70 = limb 1 bit 6
+    assert lines["poly"] == "poly 3 2 0 0 1"                           # Polynomial::from_coefficients_vec / degree / is_zero
 
 
 def test_cxx_ecc_composer_matches_python_mirror(tmp_path):

@@ -306,3 +306,40 @@ def test_bucket_reduction_chunk_sizes(ctx, oracle, monkeypatch, k_log):
     finally:
         ctx.srs_free(srs)
         ctx.srs_free(srs_pre)
+
+
+@pytest.mark.parametrize("n", [1, 7, 8, 9, 100, 1000, 5000])
+def test_pippenger_projective_bases(ctx, oracle, n):
+    """`multiscalar_mul::pippenger` (iterator form over G1Projective, SURVEY.md §8a a13) through pb200_pippenger_g1: bases
+    (x·z, y·z, z) with random z per point — and the identity (Z = 0) at a few positions — give the group element the oracle's
+    msm_variable_base gives on the affine points (identity terms dropped)."""
+    import plonk_prototype_b200 as pb
+    pts = oracle.synthetic_bases(n)                                    # (n, 12) affine, Montgomery
+    s = oracle.fr_to_mont(oracle.random_fr(0xA13 + n, n))
+    g = model.splitmix64_stream(0x2A13 + n)
+    zs = []
+    while len(zs) < n:
+        v = 0
+        for i in range(6):
+            v |= next(g) << (64 * i)
+        v &= (1 << 381) - 1
+        if 0 < v < model.P:
+            zs.append(v)
+    z = oracle.ints_to_limbs(zs, 6)
+    xyz = np.concatenate([oracle.fp_mul(np.ascontiguousarray(pts[:, :6]), z), oracle.fp_mul(np.ascontiguousarray(pts[:, 6:]), z), z], axis=1)
+    ident = [i for i in (0, 3, n - 1) if i < n and n > 1][: max(0, min(3, n - 1))]
+    for i in ident:
+        xyz[i, 12:] = 0                                                 # Z = 0: the identity, whatever X and Y hold
+    got = aff(oracle, pb.pippenger(xyz, s, ctx))
+    s_ref = s.copy()
+    s_ref[ident] = 0
+    want = aff(oracle, oracle.msm_variable_base(pts, s_ref, threads=8))
+    assert got == want
+
+
+def test_pippenger_empty_and_all_identity(ctx, oracle):
+    import plonk_prototype_b200 as pb
+    assert aff(oracle, pb.pippenger(np.zeros((0, 18), np.uint64), np.zeros((0, 4), np.uint64), ctx)) is None
+    xyz = np.zeros((5, 18), np.uint64)
+    xyz[:, 6] = 1
+    assert aff(oracle, pb.pippenger(xyz, oracle.fr_to_mont(oracle.random_fr(5, 5)), ctx)) is None

@@ -315,3 +315,43 @@ def test_reference_ecc_gadgets_on_the_composer_mirror():
     assert c3.variables == m3.values and [list(w) for w in (c3.w_l, c3.w_r, c3.w_o, c3.w_4)] == m3.w and m3.check()
     for k in pm.SELECTORS:
         assert c3.q[k] == m3.q[k], k
+
+
+def test_polynomial_wrapper_host_logic():
+    """`Polynomial::from_coefficients_vec` truncates the zero coefficients at the top; `degree()` is 0 for the zero polynomial
+    (dusk-plonk 0.8 `fft/polynomial.rs`).  No GPU involved: the arithmetic entry points are covered by the -m gpu tests."""
+    import numpy as np
+    import plonk_prototype_b200 as pb
+    c = np.zeros((6, 4), np.uint64)
+    c[0, 0], c[3, 2] = 5, 7
+    p = pb.Polynomial.from_coefficients_vec(c)
+    assert len(p) == 4 and p.degree() == 3 and not p.is_zero()
+    z = pb.Polynomial.from_coefficients_vec(np.zeros((3, 4), np.uint64))
+    assert z.is_zero() and z.degree() == 0 and len(z) == 0 and pb.Polynomial.zero().is_zero()
+
+
+def test_opening_key_bytes_round_trip():
+    """`OpeningKey::to_bytes` / from_bytes (plonk-prototype_b200/serial.py): G ‖ H ‖ β·H in the compressed zcash encodings.
+    β·H comes from the library's host-side G2 arithmetic (pb200_opening_key_from_tau, no GPU) and must equal the model's
+    τ·H; decompression (an Fp2 square root) must return the same limbs."""
+    import plonk_prototype_b200 as pb
+    from plonk_prototype_b200 import serial
+    for tau in (5, 0xB200B200B200, pm.R - 2):
+        beta_h = pb.opening_key_from_tau(pb.scalars_to_mont([tau])[0])
+        b = serial.opening_key_to_bytes(beta_h)
+        assert len(b) == 240 and b[:48] == model.g1_compress(model.G1_GEN)
+        want = pm.g2_mul(pm.G2_GEN, tau)
+        x1, x0 = int.from_bytes(bytes([b[144] & 0x1F]) + b[145:192], "big"), int.from_bytes(b[192:240], "big")
+        assert (x0, x1) == want[0]
+        assert (serial.opening_key_from_bytes(b) == beta_h).all()
+        gx1, gx0 = int.from_bytes(bytes([b[48] & 0x1F]) + b[49:96], "big"), int.from_bytes(b[96:144], "big")
+        assert (gx0, gx1) == pm.G2_GEN[0]
+    bad = bytearray(b)
+    bad[200] ^= 1
+    try:
+        serial.opening_key_from_bytes(bytes(bad))
+        raised = False
+    except AssertionError:
+        raised = True
+    # a flipped bit gives either a point off the curve (assertion) or another point — never the same key
+    assert raised or not (serial.opening_key_from_bytes(bytes(bad)) == beta_h).all()

@@ -506,3 +506,82 @@ def test_check_hash_inputs_circuit_proves_and_verifies(ctx, oracle):
     assert not pb.verify(vk, n, label, proof, pos, mont([-(pb.poseidon.hash(inputs) + 1)]), bh)
     want_proof, want_vk, _, _ = oracle.plonk_prove(sel, wires, vals, pos, piv, srs_host, label, threads=8)
     assert vk == want_vk and proof == want_proof
+
+
+def test_polynomial_and_evaluations_wrappers(ctx):
+    """`fft::Polynomial` / `fft::Evaluations` mirrors (SURVEY.md §8a a8): evaluate and ruffini against the model's Horner /
+    Ruffini, interpolate = ifft with the zero top coefficients dropped, commit(&Polynomial) = commit(coefficients)."""
+    import plonk_prototype_b200 as pb
+    n = 300
+    coeffs = model.random_fr(0xA8, n)
+    poly = pb.Polynomial.from_coefficients_vec(mont(coeffs + [0, 0, 0]), ctx)
+    assert poly.degree() == n - 1 and len(poly) == n and not poly.is_zero()
+    z = model.random_fr(0xA9, 1)[0]
+    assert (poly.evaluate(mont([z])[0]) == mont([pm.poly_eval(coeffs, z)])[0]).all()
+    q = poly.ruffini(mont([z])[0])
+    assert q.degree() == n - 2 and (q.coeffs == mont(pm.ruffini(coeffs, z))).all()
+    zero = pb.Polynomial.from_coefficients_vec(mont([0, 0]), ctx)
+    assert zero.is_zero() and zero.degree() == 0 and not zero.evaluate(mont([z])[0]).any() and zero.ruffini(mont([z])[0]).is_zero()
+    # Evaluations: values of a degree-9 polynomial over a 16-point domain interpolate back to its 10 coefficients
+    small = model.random_fr(0xAA, 10)
+    dom = pb.EvaluationDomain(16, ctx)
+    ev = pb.Evaluations.from_vec_and_domain(dom.fft(mont(small)), dom)
+    back = ev.interpolate()
+    assert back.degree() == 9 and (back.coeffs == mont(small)).all()
+    pp = pb.PublicParameters(n - 1, 0xB200, ctx)
+    try:
+        # (projective triples of two runs may differ — bucket order is not fixed — the group element may not)
+        assert pb.g1_to_bytes(ctx.msm(pp.srs, poly.coeffs)) == pb.g1_to_bytes(ctx.msm(pp.srs, mont(coeffs)))
+    finally:
+        pp.close()
+    ck = pb.CommitKey(model_points(8), ctx)
+    try:
+        small8 = pb.Polynomial.from_coefficients_vec(mont(model.random_fr(0xAB, 8)), ctx)
+        assert pb.g1_to_bytes(ck.commit(small8)) == pb.g1_to_bytes(ck.commit(small8.coeffs))
+    finally:
+        ck.close()
+
+
+def model_points(n):
+    """n packed affine points i·G (Montgomery limbs) from the big-int model."""
+    out, cur = [], model.G1_GEN
+    for _ in range(n):
+        out.append(np.concatenate([mont_fp(cur[0]), mont_fp(cur[1])]))
+        cur = model.g1_add(cur, model.G1_GEN)
+    return np.stack(out)
+
+
+
+def test_public_parameters_raw_bytes_round_trip(ctx):
+    """`PublicParameters::to_raw_bytes` → `from_slice_unchecked` (plonk-prototype_b200/serial.py): 240-byte opening key, u64
+    count, 97 bytes per point whose first 96 are the Montgomery image of τ^i·G (checked against the model for the first
+    points); the reloaded parameters commit to the same bytes and verify the same proof."""
+    import plonk_prototype_b200 as pb
+    n, tau = 64, 0x7A05
+    pp = pb.PublicParameters(n - 1, tau, ctx)
+    try:
+        raw = pp.to_raw_bytes()
+        assert len(raw) == 240 + 8 + 97 * n and int.from_bytes(raw[240:248], "little") == n
+        cur = model.G1_GEN
+        for i in range(4):
+            rec = raw[248 + 97 * i: 248 + 97 * (i + 1)]
+            want = np.concatenate([mont_fp(cur[0]), mont_fp(cur[1])])
+            assert (np.frombuffer(rec[:96], dtype=np.uint64) == want).all() and rec[96] == 0
+            cur = model.g1_mul(cur, tau)
+        coeffs = mont(model.random_fr(0x5E, n))
+        pp2 = pb.PublicParameters.from_slice_unchecked(raw, ctx)
+        try:
+            assert pp2.n_points == n and (pp2.beta_h == pp.beta_h).all()
+            assert pb.g1_to_bytes(ctx.msm(pp2.srs, coeffs)) == pb.g1_to_bytes(ctx.msm(pp.srs, coeffs))
+            var = pb.serial.commit_key_to_var_bytes(ctx, pp2.srs)
+            assert len(var) == 48 * n and var[:48] == model.g1_compress(model.G1_GEN) and var[48:96] == model.g1_compress(model.g1_mul(model.G1_GEN, tau))
+        finally:
+            pp2.close()
+        with pytest.raises(ValueError):
+            pb.PublicParameters.from_slice_unchecked(raw[:-1], ctx)
+    finally:
+        pp.close()
+
+
+def mont_fp(v):
+    return np.array([(v * (1 << 384) % model.P >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(6)], dtype=np.uint64)
