@@ -145,7 +145,7 @@ struct Field {
         S[H - 1] = cc::pack64(cc::lo32(S[H - 1]), cc::addc(cc::hi32(S[H - 1]), 0));
         redc_step(D, S);
     }
-    PB_HD static Field mul_inline(const Field &a, const Field &b) {
+    PB_HD static Field mul_unreduced(const Field &a, const Field &b) {   // a·b/R + (< p), not brought below p: see mul_lazy
         uint64_t A[H], B[H];
 #pragma unroll
         for (int k = 0; k < H; k++) {
@@ -169,8 +169,49 @@ struct Field {
             r.l[k] = cc::addc_cc(x, y);
         }
         r.l[N - 1] = cc::addc(cc::hi32(A[H - 1]), 0);
-        return reduce_once(r);
+        return r;
     }
+    PB_HD static Field mul_inline(const Field &a, const Field &b) { return reduce_once(mul_unreduced(a, b)); }
+
+    // ---- lazy representation: values in [0, 2p) (fields with a spare bit: 2p < 2^(32N)) --------------------------------
+    // The Montgomery product of a CANONICAL a (< p) and any b < 2p is a·b/R + (< p) < (2p/R + 1)·p < 2p, so it needs no
+    // final subtraction when the next operation accepts [0, 2p); the running value of the word-serial loop is bounded by
+    // a + p < 2p as in the canonical case (b is the operand scanned limb by limb, its size does not enter).  Additions and
+    // subtractions are taken mod 2p.  canonical() brings a lazy value back to [0, p).
+    PB_HD static constexpr uint32_t mod2(int i) { return (P::mod(i) << 1) | (i ? (P::mod(i - 1) >> 31) : 0u); }
+    PB_HD static Field mul_lazy(const Field &a_canonical, const Field &b) { return mul_unreduced(a_canonical, b); }
+    PB_HD static Field add_lazy(const Field &a, const Field &b) {   // a, b < 2p → (a + b) mod 2p
+        Field s;
+        s.l[0] = cc::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) s.l[i] = cc::addc_cc(a.l[i], b.l[i]);
+        s.l[N - 1] = cc::addc_cc(a.l[N - 1], b.l[N - 1]);
+        const uint32_t carry = cc::addc(0, 0);           // 4p may not fit 32N bits (Fr has one spare bit): keep the carry-out
+        Field d;
+        d.l[0] = cc::sub_cc(s.l[0], mod2(0));
+#pragma unroll
+        for (int i = 1; i < N; i++) d.l[i] = cc::subc_cc(s.l[i], mod2(i));
+        const uint32_t borrow = cc::subc(0, 0);          // all-ones when the low 32N bits are below 2p
+        const bool keep = borrow != 0 && carry == 0;      // the sum is already below 2p
+        Field r;
+#pragma unroll
+        for (int i = 0; i < N; i++) r.l[i] = keep ? s.l[i] : d.l[i];
+        return r;
+    }
+    PB_HD static Field sub_lazy(const Field &a, const Field &b) {   // a, b < 2p → (a − b) mod 2p
+        Field d;
+        d.l[0] = cc::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) d.l[i] = cc::subc_cc(a.l[i], b.l[i]);
+        const uint32_t mask = cc::subc(0, 0);
+        Field r;
+        r.l[0] = cc::add_cc(d.l[0], mod2(0) & mask);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = cc::addc_cc(d.l[i], mod2(i) & mask);
+        r.l[N - 1] = cc::addc(d.l[N - 1], mod2(N - 1) & mask);
+        return r;
+    }
+    PB_HD Field canonical() const { return reduce_once(*this); }   // [0, 2p) → [0, p)
     // operator*: fully inlined in the throughput kernels; translation units that define
     // PB_FIELD_NOINLINE_MUL (the latency-bound tail kernels) call one shared copy instead, which shrinks their
     // code ~10× (cold instruction fetch dominated those single-warp kernels) and their register count.

@@ -588,6 +588,7 @@ static int ntt_run(pb200_ctx *ctx, Fr *data, uint32_t L, int inverse, int coset,
                 if (pl->tma && !force_legacy) {
                     NttPassTma tp = pl->tpass[i];
                     tp.batch_log = L;
+                    tp.last = (i == pl->n_pass - 1);
                     PB_TRY(ntt_launch_tma(ctx, tp, src + ((size_t)b0 << L), dst + ((size_t)b0 << L), L, blocks, nb));
                     continue;
                 }

@@ -11,6 +11,9 @@
 //     bank groups in the staging loop, every round with b_lo ≥ 1 and the final write-back (only the last round's load is 2-way);
 //   * the butterfly twiddles of all rounds are staged into shared memory by one cp.async.bulk (UBLKCP) from a compact
 //     per-round image built with the plan, so the rounds issue no global loads at all;
+//   * between the passes of a transform the scalars stay in the lazy range [0, 2r) (field.cuh): sums and differences are taken
+//     mod 2r and the product by a canonical twiddle needs no final subtraction — 17 instructions fewer per multiplication on a
+//     kernel bound by dispatch slots; the last pass stores canonical values;
 //   * the bit reversal and the inter-pass twiddle / coset factor are applied in registers after the last round, the
 //     results go to shared memory at their output row, and one elected thread issues the tensor store.
 // Used for transforms of 2^12 … 2^27 points (two passes up to 2^18, three above; S ∈ 6…9); everything else, and the
@@ -94,6 +97,18 @@ __device__ __forceinline__ void sts_fr(uint32_t addr, const Fr &v) {
     sts128(addr ^ 16u, make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]));
 }
 
+// Butterflies on the lazy representation [0, 2r) (field.cuh): the product by the canonical twiddle needs no final subtraction.
+__device__ __forceinline__ void bfly_lz(Fr &a, Fr &b, const Fr &w) {
+    const Fr s = Fr::add_lazy(a, b), d = Fr::sub_lazy(a, b);
+    a = s;
+    b = Fr::mul_lazy(w, d);
+}
+__device__ __forceinline__ void bfly1_lz(Fr &a, Fr &b) {
+    const Fr s = Fr::add_lazy(a, b);
+    b = Fr::sub_lazy(a, b);
+    a = s;
+}
+
 }  // namespace tma
 
 struct NttPassTma {
@@ -105,6 +120,7 @@ struct NttPassTma {
     uint32_t load_mode;   // 0 none | 2 × l_full[natural input index]                           (type 0, coset_fft)
     uint32_t store_mode;  // 0 none | 4 × s_full[(k << ncol_log) + col] (type 0) | 5 × s_full[natural output index] (type 1)
     uint32_t batch_log;   // vectors of a batch are 2^batch_log scalars apart (blockIdx.y)
+    uint32_t last;        // last pass of the transform: results leave in canonical form (between passes they stay in [0, 2r))
     uint32_t tw_bytes;    // size of the twiddle image
     const Fr *tw_img;     // per-round compact butterfly twiddles (ntt_tw_image_kernel)
     const Fr *l_full, *s_full;
@@ -218,7 +234,7 @@ ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
             const Fr f = f_next;
             const uint32_t i2 = min(i + NTHR, T - 1);   // the factor of the next iteration travels during this multiply
             f_next = tma::ldg_fr_pinned(lf + (((uint64_t)(i2 >> 2) << p.ncol_log) + (i2 & 3u)));
-            tma::sts_fr(off, tma::lds_fr(off) * f);
+            tma::sts_fr(off, Fr::mul_lazy(f, tma::lds_fr(off)));
         }
         __syncthreads();
     }
@@ -234,17 +250,17 @@ ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
         for (int e = 0; e < 8; e++) a[e] = tma::lds_fr(tile + tma::tile_off(xbase | ((uint32_t)e << b_lo), c));
         {
 #pragma unroll
-            for (int e = 0; e < 4; e++) bfly(a[e], a[e + 4], tma::lds_fr(tw_off + ((((uint32_t)e << b_lo) + v) << 5)));
+            for (int e = 0; e < 4; e++) tma::bfly_lz(a[e], a[e + 4], tma::lds_fr(tw_off + ((((uint32_t)e << b_lo) + v) << 5)));
             const uint32_t s2 = tw_off + ((4u << b_lo) << 5);
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const Fr w = tma::lds_fr(s2 + ((((uint32_t)e << b_lo) + v) << 5));
-                bfly(a[e], a[e + 2], w);
-                bfly(a[e + 4], a[e + 6], w);
+                tma::bfly_lz(a[e], a[e + 2], w);
+                tma::bfly_lz(a[e + 4], a[e + 6], w);
             }
             const Fr w3 = tma::lds_fr(tw_off + (((6u << b_lo) + v) << 5));
 #pragma unroll
-            for (int e = 0; e < 8; e += 2) bfly(a[e], a[e + 1], w3);
+            for (int e = 0; e < 8; e += 2) tma::bfly_lz(a[e], a[e + 1], w3);
         }
 #pragma unroll
         for (int e = 0; e < 8; e++) tma::sts_fr(tile + tma::tile_off(xbase | ((uint32_t)e << b_lo), c), a[e]);
@@ -278,19 +294,19 @@ ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
         for (int e = 0; e < PF; e++) f[e] = tma::ldg_fr_pinned(factor_at(e));
     }
     if (b_top >= 2) {
-        bfly1(a[0], a[4]);
+        tma::bfly1_lz(a[0], a[4]);
 #pragma unroll
-        for (int e = 1; e < 4; e++) bfly(a[e], a[e + 4], tma::lds_fr(tw_off + ((uint32_t)(e - 1) << 5)));
+        for (int e = 1; e < 4; e++) tma::bfly_lz(a[e], a[e + 4], tma::lds_fr(tw_off + ((uint32_t)(e - 1) << 5)));
     }
     if (b_top >= 1) {
         const Fr w4 = tma::lds_fr(tw_off + 32u);
-        bfly1(a[0], a[2]);
-        bfly1(a[4], a[6]);
-        bfly(a[1], a[3], w4);
-        bfly(a[5], a[7], w4);
+        tma::bfly1_lz(a[0], a[2]);
+        tma::bfly1_lz(a[4], a[6]);
+        tma::bfly_lz(a[1], a[3], w4);
+        tma::bfly_lz(a[5], a[7], w4);
     }
 #pragma unroll
-    for (int e = 0; e < 8; e += 2) bfly1(a[e], a[e + 1]);
+    for (int e = 0; e < 8; e += 2) tma::bfly1_lz(a[e], a[e + 1]);
     // bit reversal + factor in registers, then to the tile at the OUTPUT row k
     if (p.store_mode) {
         if (!EARLY) {
@@ -299,13 +315,14 @@ ntt_pass_tma_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_con
         }
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            const Fr val = a[e] * f[e % PF];
+            Fr val = Fr::mul_lazy(f[e % PF], a[e]);
             if (e + PF < 8) f[e % PF] = tma::ldg_fr_pinned(factor_at(e + PF));
+            if (p.last) val = val.canonical();
             tma::sts_fr(tile + tma::tile_off(out_row(e), c), val);
         }
     } else {
 #pragma unroll
-        for (int e = 0; e < 8; e++) tma::sts_fr(tile + tma::tile_off(out_row(e), c), a[e]);
+        for (int e = 0; e < 8; e++) tma::sts_fr(tile + tma::tile_off(out_row(e), c), p.last ? a[e].canonical() : a[e]);
     }
     tma::fence_proxy_async();   // generic-proxy writes above → visible to the async proxy (the tensor store)
     __syncthreads();

@@ -4,6 +4,33 @@
 #include "../../plonk-prototype_b200/csrc/field.cuh"
 #include <cstddef>
 #include <cstring>
+// x + p as a plain multi-limb addition (no reduction): lifts a canonical value into the upper half of the lazy range [0, 2p)
+template <class F> struct ParamsOf;
+template <> struct ParamsOf<Fr> { typedef FrParams T; };
+template <> struct ParamsOf<Fp> { typedef FpParams T; };
+template <class F> static F lift(const F &x) {
+    F r;
+    uint64_t c = 0;
+    for (int i = 0; i < F::N; i++) {
+        const uint64_t t = (uint64_t)x.l[i] + ParamsOf<F>::T::mod(i) + c;
+        r.l[i] = (uint32_t)t;
+        c = t >> 32;
+    }
+    return r;   // x < p ⇒ x + p < 2p < 2^(32N): no carry out
+}
+// is v < 2p ?  (v − 2p borrows)
+template <class F> static bool below_2p(const F &v) {
+    int64_t borrow = 0;
+    for (int i = 0; i < F::N; i++) {
+        const int64_t t = (int64_t)v.l[i] - (int64_t)F::mod2(i) - borrow;
+        borrow = t < 0;
+    }
+    return borrow != 0;
+}
+template <class F> static F checked(const F &v) {
+    if (!below_2p(v)) __builtin_trap();     // a lazy operation left its range
+    return v.canonical();
+}
 template <class F> static void binop(int op, const uint32_t *a, const uint32_t *b, uint32_t *o, size_t n) {
     for (size_t i = 0; i < n; i++) {
         F x, y, z;
@@ -18,6 +45,10 @@ template <class F> static void binop(int op, const uint32_t *a, const uint32_t *
             case 5: z = x.inv(); break;
             case 6: z = x.neg(); break;
             case 7: z = x.sqr(); break;
+            // lazy representation [0, 2p): operands taken from both halves of the range, results must stay inside it
+            case 9: z = checked(F::mul_lazy(x, lift(y))); if (z != checked(F::mul_lazy(x, y))) __builtin_trap(); break;
+            case 10: z = checked(F::add_lazy(lift(x), lift(y))); if (z != checked(F::add_lazy(x, lift(y))) || z != checked(F::add_lazy(lift(x), y)) || z != checked(F::add_lazy(x, y))) __builtin_trap(); break;
+            case 11: z = checked(F::sub_lazy(lift(x), lift(y))); if (z != checked(F::sub_lazy(x, lift(y))) || z != checked(F::sub_lazy(lift(x), y)) || z != checked(F::sub_lazy(x, y))) __builtin_trap(); break;
             default: z = F::one();
         }
         memcpy(o + F::N * i, z.l, 4 * F::N);

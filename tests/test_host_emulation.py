@@ -123,3 +123,23 @@ def test_g1_group_law_matches_model(emu, oracle):
     assert _affine_ints(oracle, _g1(emu, 5, P, Q)) == [model.g1_add(model.g1_add(model.g1_add(a, b), b), model.g1_neg(b))
                                                         for a, b in zip(MP, MQ)]
     assert _affine_ints(oracle, _g1(emu, 6, P, Q)) == MQ              # identity accumulator paths
+
+
+def test_lazy_representation_matches_oracle(emu, oracle):
+    """Field::{mul_lazy, add_lazy, sub_lazy} (values in [0, 2p), the arithmetic of the TMA NTT kernel between its passes):
+    operands from both halves of the range — x and x + p — give the same canonical result as the oracle's modular operation,
+    and every intermediate stays below 2p (the harness traps otherwise).  Fr has ONE spare bit, so x + y can exceed 2^256:
+    the carry-out case is part of the sample (values next to r)."""
+    n = 4000
+    a, b = oracle.random_fr(21, n), oracle.random_fr(22, n)
+    edge = oracle.ints_to_limbs([0, 1, model.R - 1, model.R - 2, model.FR_MONT_R, (1 << 255) % model.R, 2**32 - 1, 2**64 - 1], 4)
+    k = len(edge)
+    a[:k * k] = np.repeat(edge, k, axis=0)
+    b[:k * k] = np.tile(edge, (k, 1))
+    assert (_run(emu, "emu_fr", 9, a, b) == oracle.fr_mul(a, b)).all()
+    assert (_run(emu, "emu_fr", 10, a, b) == oracle.fr_add(a, b)).all()
+    assert (_run(emu, "emu_fr", 11, a, b) == oracle.fr_sub(a, b)).all()
+    fa, fb = _rand_fp(oracle, 23, 1000), _rand_fp(oracle, 24, 1000)
+    assert (_run(emu, "emu_fp", 9, fa, fb) == oracle.fp_mul(fa, fb)).all()
+    assert (_run(emu, "emu_fp", 10, fa, fb) == oracle.fp_add(fa, fb)).all()
+    assert (_run(emu, "emu_fp", 11, fa, fb) == oracle.fp_sub(fa, fb)).all()
