@@ -245,7 +245,7 @@ struct Field {
         S[H - 1] = cc::pack64(cc::lo32(S[H - 1]), cc::addc(cc::hi32(S[H - 1]), 0));
         redc_step(D, S);
     }
-    PB_HD static Field sqr_inline(const Field &x) {
+    PB_HD static Field sqr_unreduced(const Field &x) {   // x²/R + (< p), not brought below p
         const uint32_t *a = x.l;
         uint32_t d[N];
         d[0] = a[0] << 1;
@@ -273,7 +273,22 @@ struct Field {
             r.l[k] = cc::addc_cc(u, v);
         }
         r.l[N - 1] = cc::addc(cc::hi32(A[H - 1]), 0);
-        return reduce_once(reduce_once(r));  // value < 3p
+        return r;
+    }
+    PB_HD static Field sqr_inline(const Field &x) { return reduce_once(reduce_once(sqr_unreduced(x))); }  // value < 3p
+    // Lazy products for fields with ≥ 3 spare bits (Fp): BOTH operands may be lazy — a·b/R + p < (4p/R + 1)·p < 2p because
+    // p/R < 1/8 — and the running value a + p < 3p (2a + p < 5p in the squaring, whose operand is pre-doubled) fits 32N bits.
+    PB_HD static Field mul_lazy2(const Field &a, const Field &b) { return mul_unreduced(a, b); }
+    PB_HD static Field sqr_lazy(const Field &a) { return sqr_unreduced(a); }
+    // ≡ 0 (mod p) for a lazy value: 0 or p
+    PB_HD bool is_zero_lazy() const {
+        uint32_t o = 0, q = 0;
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            o |= l[i];
+            q |= l[i] ^ P::mod(i);
+        }
+        return o == 0 || q == 0;
     }
     PB_HD Field sqr() const {
         if (P::SPARE_BITS >= 3) {

@@ -90,6 +90,37 @@ PB_HD void g1_madd(G1Xyzz &acc, const G1Affine &p) {
     acc.zz = acc.zz * pp;
     acc.zzz = acc.zzz * ppp;
 }
+// The same mixed addition on the lazy representation (field.cuh): acc's coordinates live in [0, 2p) between additions, no
+// product is brought below p (Fp has three spare bits), sums and differences are taken mod 2p.  Used by the accumulation
+// kernel only, which canonicalises a run's sum before it leaves the registers.  The identity is still ZZ = 0 exactly: a
+// product is ≡ 0 only if a factor is, and the one factor that can be (P ≡ 0: equal or opposite points) returns early.
+PB_HD void g1_madd_lazy(G1Xyzz &acc, const G1Affine &p) {
+    if (acc.is_identity()) {
+        acc = G1Xyzz::from_affine(p);
+        return;
+    }
+    const Fp u2 = Fp::mul_lazy2(p.x, acc.zz), s2 = Fp::mul_lazy2(p.y, acc.zzz);
+    const Fp pp_ = Fp::sub_lazy(u2, acc.x), r = Fp::sub_lazy(s2, acc.y);
+    if (pp_.is_zero_lazy()) {
+        if (r.is_zero_lazy()) acc = g1_dbl_affine(p);  // same point
+        else acc = G1Xyzz::identity();                 // opposite points
+        return;
+    }
+    const Fp pp = Fp::sqr_lazy(pp_), ppp = Fp::mul_lazy2(pp_, pp), q = Fp::mul_lazy2(acc.x, pp);
+    const Fp x3 = Fp::sub_lazy(Fp::sub_lazy(Fp::sqr_lazy(r), ppp), Fp::add_lazy(q, q));
+    acc.y = Fp::sub_lazy(Fp::mul_lazy2(r, Fp::sub_lazy(q, x3)), Fp::mul_lazy2(acc.y, ppp));
+    acc.x = x3;
+    acc.zz = Fp::mul_lazy2(acc.zz, pp);
+    acc.zzz = Fp::mul_lazy2(acc.zzz, ppp);
+}
+PB_HD G1Xyzz g1_canonical(const G1Xyzz &a) {
+    G1Xyzz r;
+    r.x = a.x.canonical();
+    r.y = a.y.canonical();
+    r.zz = a.zz.canonical();
+    r.zzz = a.zzz.canonical();
+    return r;
+}
 // a + b, both XYZZ (add-2008-s): 12M + 2S on the common path.
 PB_HD G1Xyzz g1_add(const G1Xyzz &a, const G1Xyzz &b) {
     if (a.is_identity()) return b;

@@ -191,14 +191,14 @@ __device__ __forceinline__ void msm_accumulate_body(const G1Affine *__restrict__
             asm volatile("prefetch.global.L2 [%0];" ::"l"(np + 64));
         }
         if (gb != cur) {
-            sink.flush(cur, acc, tl, false);
+            sink.flush(cur, g1_canonical(acc), tl, false);
             cur = gb;
             tl = false;
             acc = G1Xyzz::identity();
         }
-        g1_madd(acc, pt);
+        g1_madd_lazy(acc, pt);   // coordinates stay in [0, 2p) while the run's sum lives in registers (g1.cuh)
     }
-    sink.flush(cur, acc, tl, next == cur);
+    sink.flush(cur, g1_canonical(acc), tl, next == cur);
     sink.finish();
 }
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const G1Affine *__restrict__ bases, const uint2 *__restrict__ entries,

@@ -48,6 +48,8 @@ template <class F> static void binop(int op, const uint32_t *a, const uint32_t *
             // lazy representation [0, 2p): operands taken from both halves of the range, results must stay inside it
             case 9: z = checked(F::mul_lazy(x, lift(y))); if (z != checked(F::mul_lazy(x, y))) __builtin_trap(); break;
             case 10: z = checked(F::add_lazy(lift(x), lift(y))); if (z != checked(F::add_lazy(x, lift(y))) || z != checked(F::add_lazy(lift(x), y)) || z != checked(F::add_lazy(x, y))) __builtin_trap(); break;
+            case 12: z = checked(F::mul_unreduced(lift(x), lift(y))); if (z != checked(F::mul_unreduced(x, lift(y))) || z != checked(F::mul_unreduced(lift(x), y))) __builtin_trap(); break;   // both operands lazy (Fp only)
+            case 13: z = checked(F::sqr_unreduced(lift(x))); if (z != checked(F::sqr_unreduced(x))) __builtin_trap(); break;
             case 11: z = checked(F::sub_lazy(lift(x), lift(y))); if (z != checked(F::sub_lazy(x, lift(y))) || z != checked(F::sub_lazy(lift(x), y)) || z != checked(F::sub_lazy(x, y))) __builtin_trap(); break;
             default: z = F::one();
         }
@@ -90,6 +92,12 @@ void emu_g1(int op, const uint32_t *p, const uint32_t *q, uint32_t *o, size_t n,
             case 3: r = g1_dbl(g1_dbl_affine(P)); break;
             case 4: r = g1_mul_small(G1Xyzz::from_affine(P), k); break;
             case 5: { r = G1Xyzz::from_affine(P); g1_madd(r, Q); g1_madd(r, Q); G1Affine nQ = Q; nQ.y = nQ.y.neg(); g1_madd(r, nQ); break; }
+            case 7: {  // the lazy mixed addition: P, then Q three times, −Q, P again (doubling path), through g1_madd_lazy
+                r = G1Xyzz::identity(); g1_madd_lazy(r, P); g1_madd_lazy(r, Q); g1_madd_lazy(r, Q); g1_madd_lazy(r, Q);
+                G1Affine nQ = Q; nQ.y = nQ.y.neg(); g1_madd_lazy(r, nQ); g1_madd_lazy(r, P);
+                if (!below_2p(r.x) || !below_2p(r.y) || !below_2p(r.zz) || !below_2p(r.zzz)) __builtin_trap();
+                r = g1_canonical(r); break; }
+            case 8: { r = G1Xyzz::identity(); g1_madd_lazy(r, P); g1_madd_lazy(r, P); G1Affine nP = P; nP.y = nP.y.neg(); g1_madd_lazy(r, nP); g1_madd_lazy(r, nP); g1_madd_lazy(r, Q); r = g1_canonical(r); break; }   // doubling, then cancellation to the identity, then Q
             case 6: { r = G1Xyzz::identity(); g1_madd(r, P); G1Affine nP = P; nP.y = nP.y.neg(); g1_madd(r, nP); g1_madd(r, Q); break; }
             default: r = G1Xyzz::identity();
         }

@@ -123,6 +123,16 @@ def test_g1_group_law_matches_model(emu, oracle):
     assert _affine_ints(oracle, _g1(emu, 5, P, Q)) == [model.g1_add(model.g1_add(model.g1_add(a, b), b), model.g1_neg(b))
                                                         for a, b in zip(MP, MQ)]
     assert _affine_ints(oracle, _g1(emu, 6, P, Q)) == MQ              # identity accumulator paths
+    # the lazy mixed addition of the accumulation kernel (coordinates in [0, 2p), harness traps when one leaves the range):
+    # P + 3Q − Q + P, incl. the pairs Q = P (tangent) and Q = −P (cancellation), and P + P − P − P + Q
+    want7 = []
+    for a, b in zip(MP, MQ):
+        r = a
+        for t in (b, b, b, model.g1_neg(b), a):
+            r = model.g1_add(r, t)
+        want7.append(r)
+    assert _affine_ints(oracle, _g1(emu, 7, P, Q)) == want7
+    assert _affine_ints(oracle, _g1(emu, 8, P, Q)) == MQ
 
 
 def test_lazy_representation_matches_oracle(emu, oracle):
@@ -143,3 +153,8 @@ def test_lazy_representation_matches_oracle(emu, oracle):
     assert (_run(emu, "emu_fp", 9, fa, fb) == oracle.fp_mul(fa, fb)).all()
     assert (_run(emu, "emu_fp", 10, fa, fb) == oracle.fp_add(fa, fb)).all()
     assert (_run(emu, "emu_fp", 11, fa, fb) == oracle.fp_sub(fa, fb)).all()
+    # Fp has three spare bits: both operands of a product may be lazy, and so may the operand of the dedicated squaring
+    top = oracle.ints_to_limbs([model.P - 1 - j for j in range(64)] + [0, 1, 2], 6)
+    fa[:67], fb[:67] = top, top[::-1].copy()
+    assert (_run(emu, "emu_fp", 12, fa, fb) == oracle.fp_mul(fa, fb)).all()
+    assert (_run(emu, "emu_fp", 13, fa, fb) == oracle.fp_mul(fa, fa)).all()
