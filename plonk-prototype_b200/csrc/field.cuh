@@ -93,6 +93,15 @@ struct Field {
         return r;
     }
     PB_HD Field neg() const { return is_zero() ? *this : (zero() - *this); }
+    // −x for x ≠ 0 (e.g. the y coordinate of a point of the prime-order subgroup): p − x, one subtraction chain
+    PB_HD Field neg_nonzero() const {
+        Field r;
+        r.l[0] = cc::sub_cc(P::mod(0), l[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = cc::subc_cc(P::mod(i), l[i]);
+        r.l[N - 1] = cc::subc(P::mod(N - 1), l[N - 1]);
+        return r;
+    }
     PB_HD Field dbl() const { return *this + *this; }
 
     // ---- multiplication: u64 column accumulators -------------------------------------------------

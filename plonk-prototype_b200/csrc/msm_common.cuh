@@ -48,7 +48,7 @@ __device__ __forceinline__ void store_fp2(uint4 *q, const Fp &a, const Fp &b) {
 __device__ __forceinline__ G1Affine load_affine(const G1Affine *bases, uint32_t idx_sign) {
     G1Affine p;
     load_fp2(reinterpret_cast<const uint4 *>(bases + (idx_sign & 0x7fffffffu)), p.x, p.y);
-    if (idx_sign >> 31) p.y = p.y.neg();
+    if (idx_sign >> 31) p.y = p.y.neg_nonzero();   // y ≠ 0 on the prime-order subgroup
     return p;
 }
 __device__ __forceinline__ G1Xyzz load_xyzz(const G1Xyzz *p) {

@@ -45,6 +45,7 @@ template <class F> static void binop(int op, const uint32_t *a, const uint32_t *
             case 5: z = x.inv(); break;
             case 6: z = x.neg(); break;
             case 7: z = x.sqr(); break;
+            case 14: z = x.is_zero() ? x : x.neg_nonzero(); break;
             // lazy representation [0, 2p): operands taken from both halves of the range, results must stay inside it
             case 9: z = checked(F::mul_lazy(x, lift(y))); if (z != checked(F::mul_lazy(x, y))) __builtin_trap(); break;
             case 10: z = checked(F::add_lazy(lift(x), lift(y))); if (z != checked(F::add_lazy(x, lift(y))) || z != checked(F::add_lazy(lift(x), y)) || z != checked(F::add_lazy(x, y))) __builtin_trap(); break;

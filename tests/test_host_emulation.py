@@ -72,6 +72,7 @@ def test_fp_matches_oracle(emu, oracle):
     assert (_run(emu, "emu_fp", 3, a, b) == oracle.fp_from_mont(a)).all()
     assert (_run(emu, "emu_fp", 4, a, b) == oracle.fp_to_mont(a)).all()
     assert (_run(emu, "emu_fp", 5, a[:32], b[:32]) == oracle.fp_inv(a[:32])).all()
+    assert (_run(emu, "emu_fp", 14, a, b) == oracle.fp_sub(np.zeros_like(a), a)).all()   # neg_nonzero = p − x (0 stays 0 in the harness)
     # dedicated squaring (triangular products on the pre-doubled operand) incl. the extreme values p−1, p−2, 2^380
     assert (_run(emu, "emu_fp", 7, a, b) == oracle.fp_mul(a, a)).all()
     top = oracle.ints_to_limbs([model.P - 1 - k for k in range(64)] + [(1 << 381) - 1 - 3 * k for k in range(64)
