@@ -79,18 +79,47 @@ struct Field {
         s.l[N - 1] = cc::addc(a.l[N - 1], b.l[N - 1]);  // a+b < 2p < 2^(32N): no carry out
         return reduce_once(s);
     }
+    // d += K·p when mask ≠ 0 (K = 1, 2), limb-wise with carry.  On the device the additions are PREDICATED (N instructions)
+    // instead of masking the constant first (2N): the kernels that use this are bound by dispatch slots.
+    template <int K>
+    PB_HD static constexpr uint32_t kp(int i) { return K == 1 ? P::mod(i) : mod2(i); }
+    template <int K>
+    PB_HD static void cond_add_kp(Field &d, uint32_t mask) {
+#if defined(__CUDA_ARCH__)
+        if constexpr (N == 8) {
+            asm volatile(
+                "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %8, 0;\n\t"
+                "@q add.cc.u32 %0, %0, %9;\n\t@q addc.cc.u32 %1, %1, %10;\n\t@q addc.cc.u32 %2, %2, %11;\n\t@q addc.cc.u32 %3, %3, %12;\n\t"
+                "@q addc.cc.u32 %4, %4, %13;\n\t@q addc.cc.u32 %5, %5, %14;\n\t@q addc.cc.u32 %6, %6, %15;\n\t@q addc.u32 %7, %7, %16;\n\t}"
+                : "+r"(d.l[0]), "+r"(d.l[1]), "+r"(d.l[2]), "+r"(d.l[3]), "+r"(d.l[4]), "+r"(d.l[5]), "+r"(d.l[6]), "+r"(d.l[7])
+                : "r"(mask), "n"(kp<K>(0)), "n"(kp<K>(1)), "n"(kp<K>(2)), "n"(kp<K>(3)), "n"(kp<K>(4)), "n"(kp<K>(5)), "n"(kp<K>(6)), "n"(kp<K>(7)));
+            return;
+        } else if constexpr (N == 12) {
+            asm volatile(
+                "{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %12, 0;\n\t"
+                "@q add.cc.u32 %0, %0, %13;\n\t@q addc.cc.u32 %1, %1, %14;\n\t@q addc.cc.u32 %2, %2, %15;\n\t@q addc.cc.u32 %3, %3, %16;\n\t"
+                "@q addc.cc.u32 %4, %4, %17;\n\t@q addc.cc.u32 %5, %5, %18;\n\t@q addc.cc.u32 %6, %6, %19;\n\t@q addc.cc.u32 %7, %7, %20;\n\t"
+                "@q addc.cc.u32 %8, %8, %21;\n\t@q addc.cc.u32 %9, %9, %22;\n\t@q addc.cc.u32 %10, %10, %23;\n\t@q addc.u32 %11, %11, %24;\n\t}"
+                : "+r"(d.l[0]), "+r"(d.l[1]), "+r"(d.l[2]), "+r"(d.l[3]), "+r"(d.l[4]), "+r"(d.l[5]), "+r"(d.l[6]), "+r"(d.l[7]), "+r"(d.l[8]),
+                  "+r"(d.l[9]), "+r"(d.l[10]), "+r"(d.l[11])
+                : "r"(mask), "n"(kp<K>(0)), "n"(kp<K>(1)), "n"(kp<K>(2)), "n"(kp<K>(3)), "n"(kp<K>(4)), "n"(kp<K>(5)), "n"(kp<K>(6)), "n"(kp<K>(7)),
+                  "n"(kp<K>(8)), "n"(kp<K>(9)), "n"(kp<K>(10)), "n"(kp<K>(11)));
+            return;
+        }
+#endif
+        d.l[0] = cc::add_cc(d.l[0], kp<K>(0) & mask);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) d.l[i] = cc::addc_cc(d.l[i], kp<K>(i) & mask);
+        d.l[N - 1] = cc::addc(d.l[N - 1], kp<K>(N - 1) & mask);
+    }
     PB_HD friend Field operator-(const Field &a, const Field &b) {
         Field d;
         d.l[0] = cc::sub_cc(a.l[0], b.l[0]);
 #pragma unroll
         for (int i = 1; i < N; i++) d.l[i] = cc::subc_cc(a.l[i], b.l[i]);
         uint32_t mask = cc::subc(0, 0);  // all-ones when a < b
-        Field r;
-        r.l[0] = cc::add_cc(d.l[0], P::mod(0) & mask);
-#pragma unroll
-        for (int i = 1; i < N - 1; i++) r.l[i] = cc::addc_cc(d.l[i], P::mod(i) & mask);
-        r.l[N - 1] = cc::addc(d.l[N - 1], P::mod(N - 1) & mask);
-        return r;
+        cond_add_kp<1>(d, mask);
+        return d;
     }
     PB_HD Field neg() const { return is_zero() ? *this : (zero() - *this); }
     // −x for x ≠ 0 (e.g. the y coordinate of a point of the prime-order subgroup): p − x, one subtraction chain
@@ -213,12 +242,8 @@ struct Field {
 #pragma unroll
         for (int i = 1; i < N; i++) d.l[i] = cc::subc_cc(a.l[i], b.l[i]);
         const uint32_t mask = cc::subc(0, 0);
-        Field r;
-        r.l[0] = cc::add_cc(d.l[0], mod2(0) & mask);
-#pragma unroll
-        for (int i = 1; i < N - 1; i++) r.l[i] = cc::addc_cc(d.l[i], mod2(i) & mask);
-        r.l[N - 1] = cc::addc(d.l[N - 1], mod2(N - 1) & mask);
-        return r;
+        cond_add_kp<2>(d, mask);
+        return d;
     }
     PB_HD Field canonical() const { return reduce_once(*this); }   // [0, 2p) → [0, p)
     // operator*: fully inlined in the throughput kernels; translation units that define

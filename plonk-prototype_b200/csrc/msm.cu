@@ -360,7 +360,16 @@ static int msm_piece(pb200_ctx *ctx, const G1Affine *bases, const uint64_t *scal
     t_sort.stop();
 
     PbTimer t_acc(ctx, "msm.accumulate");
-    msm_accumulate_kernel<<<(lvl_threads[0] + 127) / 128, 128, 0, st>>>(bases, entries, meta + 0, cfg.L1, buckets, gbA, ptA, meta + 1);
+    // 166 registers let three CTAs share an SM; two measured faster (profiles/pipe_model_experiments_r02.txt §5), and the grid is
+    // sized in whole waves of two: 80 KiB of (unused) dynamic shared memory per CTA keeps it at two.  PB200_MSM_ACC_CTAS=3 lifts it.
+    static const bool acc_three = getenv("PB200_MSM_ACC_CTAS") && atoi(getenv("PB200_MSM_ACC_CTAS")) == 3;
+    const size_t acc_smem = acc_three ? 0 : 80 * 1024;
+    static bool acc_attr = false;
+    if (!acc_attr) {
+        PB_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        acc_attr = true;
+    }
+    msm_accumulate_kernel<<<(lvl_threads[0] + 127) / 128, 128, acc_smem, st>>>(bases, entries, meta + 0, cfg.L1, buckets, gbA, ptA, meta + 1);
     PB_LAUNCHED(ctx);
     t_acc.stop();
     PbTimer t_fix(ctx, "msm.partials");
